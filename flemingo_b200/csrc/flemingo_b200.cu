@@ -1,0 +1,977 @@
+// flemingo_b200.cu -- sm_100a kernels + C ABI (include/flemingo_b200.h) for FLEMINGO's placement hot path.
+//
+// What the kernels compute is specified by the reference C extension (paths relative to
+// /root/reference/extensions/multiplacement/src):
+//   K1  recognizer score rows      organism/recognizer.c:130-168 (PSSM), :187-589 (shape), _aux.c:184-217
+//   K2  gap-energy table + chain DP organism/connector.c:31-66, organism/organism.c:321-393
+//       argmax + traceback          _aux.c:149-158, organism/organism.c:398-427
+//   K3  fitness statistic           src/objects/organism_object.py:848-956 (reference does this in numpy)
+//
+// Arithmetic contract: every value is an IEEE double produced by the same operations in the same operand
+// order as the reference ((prev[k] + G[j-k]) + R[j], left-to-right score sums, IEEE division), compiled with
+// -fmad=false, so energies, node scores and offsets are bit-identical, including the reference's tie rule
+// (smallest k per stage, smallest j at the end).  Two identities make that cheap:
+//   (1) x -> fl(x + r) is monotone, so  max_k fl(fl(prev[k]+G[j-k]) + R[j]) == fl(max_k fl(prev[k]+G[j-k]) + R[j]):
+//       the inner loop needs one add and one max per cell;
+//   (2) the winning k is only needed on the optimal path, so the forward pass keeps no argmax; the traceback
+//       re-scans one column per stage for the FIRST k that reproduces the stored value bit for bit.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "flemingo_b200.h"
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CK(call)                                                                               \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) return fail(FL_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// device-side constants and small structs
+// ------------------------------------------------------------------------------------------------
+#define T_MGW 0
+#define T_PROT 1024
+#define T_ROLL 2048
+#define T_HELT 4096
+#define T_DEN 6144
+
+#define BIG_NEG (-1e10)
+#define BIG_POS (1e10)
+
+constexpr int kRowTiles = 4;              // rows per lane in the simple DP kernel (32*kRowTiles rows per pass)
+constexpr int kPadLo = 32 * kRowTiles;    // -inf padding below G[0]: j-k reaches -(32*kRowTiles-1) on diagonal tiles
+constexpr int kPadHi = 32 * kRowTiles;    // padding above G[P-1]: rows of the last pass may exceed P-1
+constexpr int kMaxSmem = 232448;          // 227 KB opt-in limit per CTA on sm_100
+
+#define ERR_NAN_NULL 1
+
+struct RecDesc {
+  int kind;  // 0 PSSM, 1 MGW, 2 ProT, 3 Roll, 4 HelT
+  int len;
+  int nb;    // number of bin edges (shape only)
+  int data;  // offset into the organism's slice of the recognizer pool (doubles)
+  int fwd;   // sum of the lengths of the recognizers before this one (organism.c:273,392)
+  int pad;
+};
+
+struct PlaceParams {
+  // population (device pointers)
+  const int *rec_begin;
+  const char *rec_type;
+  const int *rec_len;
+  const int *rec_nb;
+  const long long *rec_data;
+  const long long *pool_begin;
+  const double *rec_pool;
+  const int *con_M;
+  const double *con_pool;
+  const long long *con_begin;  // [n_org] for this class
+  const int *sum_len;
+  // sequence set
+  const unsigned *packed;
+  const unsigned *unk;
+  const int *word_off;
+  const int *unk_off;
+  const int *order;
+  int class_begin, class_count, S, n_seq_total;
+  // data tables
+  const double *tables;
+  // outputs
+  double *E;
+  int *gaps;
+  double *rsc;
+  double *csc;
+  int max_rec;
+  int *err_flag;
+  // plan
+  int seqs_per_cta, chunks;
+  int pool_stride, g_stride, row_stride, code_stride, nrows;
+};
+
+__device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xfff0000000000000LL); }
+
+// Score of one recognizer at one offset.  `codes` already points at the recognizer's first admissible base
+// (sequence + forward offset, organism.c:328).  Codes: 0..3 = A,G,C,T; 4 = any other byte.
+__device__ __forceinline__ double score_rec(const RecDesc &r, const double *s_pool, const unsigned char *codes, int pos,
+                                            const double *__restrict__ tables, int &err) {
+  const unsigned char *c = codes + pos;
+  if (r.kind == 0) {
+    // recognizer.c:130-168: left-to-right sum from 0.0; an unknown byte adds nothing
+    const double *m = s_pool + r.data;
+    double s = 0.0;
+    for (int col = 0; col < r.len; ++col) {
+      const int b = c[col];
+      if (b < 4) s += m[4 * col + b];
+    }
+    return s;
+  }
+  const int np = r.len - 4;
+  double score;
+  // pentamer index: sum code * 4^(4-k), unknown bytes count as 0 (recognizer.c:219-241 has no default case)
+  int idx = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) idx = idx * 4 + (c[k] & 3) * (c[k] < 4);
+  if (r.kind <= 2) {
+    // _aux.c:211-217
+    const double *tab = tables + (r.kind == 1 ? T_MGW : T_PROT);
+    double sum = 0.0;
+    for (int j = 0; j < np; ++j) {
+      idx = ((idx << 2) | ((c[j + 4] & 3) * (c[j + 4] < 4))) & 1023;
+      sum += __ldg(tab + idx);
+    }
+    score = sum / (double)np;
+  } else {
+    // _aux.c:203-209 on pent = [TAB[idx_0..]] ++ [TAB[1024+idx_0..]] (recognizer.c:447-450)
+    const double *tab = tables + (r.kind == 3 ? T_ROLL : T_HELT);
+    const int idx0 = ((idx << 2) | ((c[4] & 3) * (c[4] < 4))) & 1023;
+    int idxl = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) idxl = idxl * 4 + (c[np - 1 + k] & 3) * (c[np - 1 + k] < 4);
+    double sum = __ldg(tab + idx0) + __ldg(tab + 1024 + idxl);
+    int id = idx;
+    for (int j = 0; j < np; ++j) {
+      id = ((id << 2) | ((c[j + 4] & 3) * (c[j + 4] < 4))) & 1023;
+      sum += __ldg(tab + id);
+    }
+    id = idx;
+    for (int j = 0; j < np; ++j) {
+      id = ((id << 2) | ((c[j + 4] & 3) * (c[j + 4] < 4))) & 1023;
+      sum += __ldg(tab + 1024 + id);
+    }
+    score = sum / (double)(2 * np + 2);
+  }
+  // _aux.c:184-190: first bin with edges[b-1] <= score < edges[b], otherwise the last bin
+  const double *nullf = s_pool + r.data;
+  const double *altf = nullf + (r.nb - 1);
+  const double *edges = altf + (r.nb - 1);
+  int b = 1;
+  for (; b < r.nb; ++b)
+    if (score >= edges[b - 1] && score < edges[b]) break;
+  if (b == r.nb) b = r.nb - 1;
+  const double n0 = nullf[b - 1];
+  double v = altf[b - 1] - n0;
+  if (v < BIG_NEG) v = BIG_NEG;
+  if (n0 != n0) err |= ERR_NAN_NULL;
+  return v;
+}
+
+// connector.c:35-66 for one gap length; D = DEN_EXPANSION
+__device__ __forceinline__ double gap_energy(const double *__restrict__ pdf, double auc, int g, int n, int eff,
+                                             const double *__restrict__ D) {
+  if (g + n + 1 <= eff) {
+    double num = __ldg(pdf + g);
+    if (num < BIG_NEG) num = BIG_NEG;
+    num -= auc;
+    const double den = (__ldg(D + (eff - (g + 1)) - 1) - __ldg(D + (n - 1) - 1) - __ldg(D + eff - (g + 1) - (n - 1) - 1)) -
+                       (__ldg(D + eff - 1) - __ldg(D + n - 1) - __ldg(D + eff - n - 1));
+    double res = num - den;
+    if (res < BIG_NEG) return BIG_NEG;
+    if (res > BIG_POS) return BIG_POS;
+    return res;
+  }
+  return BIG_NEG;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1+K2 fused, exact fp64: one CTA = one organism x a chunk of sequences of one length class;
+// one warp = one (organism, sequence) pair at a time.
+// ------------------------------------------------------------------------------------------------
+template <bool TRACE>
+__global__ void __launch_bounds__(256) place_exact_kernel(const PlaceParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int o = blockIdx.x / p.chunks;
+  const int chunk = blockIdx.x - o * p.chunks;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int rb = p.rec_begin[o];
+  const int n = p.rec_begin[o + 1] - rb;
+  const int S = p.S;
+  const int sumL = p.sum_len[o];
+  const int P = S - sumL + 1;
+  const int eff = S - sumL + n;
+
+  double *s_pool = reinterpret_cast<double *>(smem_raw);
+  double *s_G = s_pool + p.pool_stride;
+  double *s_rows = s_G + (size_t)(p.max_rec - 1) * p.g_stride;
+  RecDesc *s_rec = reinterpret_cast<RecDesc *>(s_rows + (size_t)nwarps * p.nrows * p.row_stride);
+  unsigned char *s_codes = reinterpret_cast<unsigned char *>(s_rec + p.max_rec);
+
+  // ---- organism prologue: tables into shared memory, gap-energy tables G[c][g] -------------------
+  {
+    const long long pb = p.pool_begin[o];
+    const int pn = (int)(p.pool_begin[o + 1] - pb);
+    for (int i = tid; i < pn; i += blockDim.x) s_pool[i] = __ldg(p.rec_pool + pb + i);
+    if (tid == 0) {
+      int fwd = 0;
+      for (int i = 0; i < n; ++i) {
+        RecDesc d;
+        const char t = p.rec_type[rb + i];
+        d.kind = (t == 'p' || t == 'P') ? 0 : (t == 'm' || t == 'M') ? 1 : (t == 't' || t == 'T') ? 2 : (t == 'r' || t == 'R') ? 3 : 4;
+        d.len = p.rec_len[rb + i];
+        d.nb = p.rec_nb[rb + i];
+        d.data = (int)(p.rec_data[rb + i] - pb);
+        d.fwd = fwd;
+        d.pad = 0;
+        fwd += d.len;
+        s_rec[i] = d;
+      }
+    }
+    const int M = p.con_M[o];
+    const double *D = p.tables + T_DEN;
+    for (int c = 0; c < n - 1; ++c) {
+      const double *pdf = p.con_pool + p.con_begin[o] + (long long)c * (2 * M + 2) + 2;
+      const double auc = __ldg(pdf + (M - 1) + (S - sumL));  // cdf pointer = pdf + max_len, max_len = M-1 (connector.c:3-4)
+      double *Gc = s_G + (size_t)c * p.g_stride;
+      for (int i = tid; i < p.g_stride; i += blockDim.x) {
+        const int g = i - kPadLo;
+        Gc[i] = (g < 0 || g >= P) ? neg_inf() : gap_energy(pdf, auc, g, n, eff, D);
+      }
+    }
+  }
+  __syncthreads();
+
+  double *rows = s_rows + (size_t)warp * p.nrows * p.row_stride;
+  unsigned char *codes = s_codes + (size_t)warp * p.code_stride;
+  int err = 0;
+
+  const int first = chunk * p.seqs_per_cta;
+  const int last = min(p.class_count, first + p.seqs_per_cta);
+  for (int si = first + warp; si < last; si += nwarps) {
+    const int seq = p.order[p.class_begin + si];
+    // ---- unpack 2-bit bases (+ unknown mask) into byte codes ------------------------------------
+    {
+      const unsigned *pw = p.packed + p.word_off[seq];
+      const unsigned *uw = p.unk + p.unk_off[seq];
+      for (int b = lane; b < S; b += 32) {
+        const unsigned w = __ldg(pw + (b >> 4));
+        const unsigned u = __ldg(uw + (b >> 5));
+        const unsigned code = (w >> (2 * (b & 15))) & 3u;
+        codes[b] = ((u >> (b & 31)) & 1u) ? 4 : (unsigned char)code;
+      }
+    }
+    __syncwarp();
+
+    // ---- stage 0: C_0 = R_0 (organism.c:381-385) ------------------------------------------------
+    for (int j = lane; j < P; j += 32) rows[j] = score_rec(s_rec[0], s_pool, codes, j, p.tables, err);
+    __syncwarp();
+
+    // ---- stages 1..n-1: C_i[j] = max_k (C_{i-1}[k] + G[j-k]) + R_i[j] (organism.c:347-369) --------
+    for (int i = 1; i < n; ++i) {
+      const double *prev = rows + (size_t)(TRACE ? (i - 1) : ((i - 1) & 1)) * p.row_stride;
+      double *cur = rows + (size_t)(TRACE ? i : (i & 1)) * p.row_stride;
+      const double *Gc = s_G + (size_t)(i - 1) * p.g_stride + kPadLo;
+      const RecDesc rd = s_rec[i];
+      const unsigned char *ci = codes + rd.fwd;
+      for (int jb = 0; jb < P; jb += 32 * kRowTiles) {
+        double acc[kRowTiles];
+#pragma unroll
+        for (int t = 0; t < kRowTiles; ++t) acc[t] = neg_inf();
+        const double *gp = Gc + jb + lane;
+        const int kend = min(P, jb + 32 * kRowTiles);
+#pragma unroll 2
+        for (int k = 0; k < kend; ++k) {
+          const double pv = prev[k];
+#pragma unroll
+          for (int t = 0; t < kRowTiles; ++t) {
+            const double cand = pv + gp[32 * t - k];
+            acc[t] = (acc[t] < cand) ? cand : acc[t];
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < kRowTiles; ++t) {
+          const int j = jb + lane + 32 * t;
+          if (j < P) cur[j] = acc[t] + score_rec(rd, s_pool, ci, j, p.tables, err);
+        }
+      }
+      __syncwarp();
+    }
+
+    // ---- first maximum of the last row (_aux.c:149-158) ------------------------------------------
+    const double *lastrow = rows + (size_t)(TRACE ? (n - 1) : ((n - 1) & 1)) * p.row_stride;
+    double bv = neg_inf();
+    int bi = 0x7fffffff;
+    for (int j = lane; j < P; j += 32) {
+      const double v = lastrow[j];
+      if (bi == 0x7fffffff || v > bv) { bv = v; bi = j; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+    }
+    const size_t pair = (size_t)o * p.n_seq_total + seq;
+    if (lane == 0) p.E[pair] = bv;
+
+    // ---- traceback (organism.c:398-427): re-scan one column per stage for the first k that reproduces
+    //      the stored value exactly -- identical to the reference's strict '<' update rule -------------
+    if (TRACE) {
+      int m = bi;
+      for (int i = n - 1; i >= 1; --i) {
+        const double *prev = rows + (size_t)(i - 1) * p.row_stride;
+        const double *Gc = s_G + (size_t)(i - 1) * p.g_stride + kPadLo;
+        const RecDesc rd = s_rec[i];
+        const double ri = score_rec(rd, s_pool, codes + rd.fwd, m, p.tables, err);
+        const double target = rows[(size_t)i * p.row_stride + m];
+        int found = -1;
+        for (int kb = 0; kb <= m && found < 0; kb += 32) {
+          const int k = kb + lane;
+          const bool hit = (k <= m) && ((prev[k] + Gc[m - k]) + ri == target);
+          const unsigned bal = __ballot_sync(0xffffffffu, hit);
+          if (bal) found = kb + __ffs(bal) - 1;
+        }
+        const int gap = found < 0 ? 0 : m - found;  // nothing ever won: the reference keeps its calloc'ed zeros
+        if (lane == 0) {
+          p.rsc[pair * p.max_rec + i] = ri;
+          p.csc[pair * p.max_rec + i - 1] = found < 0 ? 0.0 : Gc[gap];
+          p.gaps[pair * p.max_rec + i] = gap;
+        }
+        m -= gap;
+      }
+      if (lane == 0) {
+        p.rsc[pair * p.max_rec] = rows[m];
+        p.gaps[pair * p.max_rec] = m;
+      }
+    }
+    __syncwarp();
+  }
+  if (err) atomicOr(p.err_flag, err);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: per-organism fitness statistic (organism_object.py:848-956).  One CTA per organism.
+// ------------------------------------------------------------------------------------------------
+__device__ double block_sum(double v, double *s_red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  __syncthreads();
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < nw; ++w) t += s_red[w];
+  return t;
+}
+
+// in-place bitonic sort of n2 (power of two) doubles by one CTA
+__device__ void block_bitonic_sort(double *a, int n2) {
+  for (int k = 2; k <= n2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const double x = a[i], y = a[l];
+          const bool up = ((i & k) == 0);
+          if ((x > y) == up) { a[i] = y; a[l] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+struct SetStat {
+  double mean, se;
+};
+
+// mean / standard error of one organism's energies on one set; `scratch` (n2 doubles) is used by the
+// trimmed variants.  lo/hi = number of elements dropped from the sorted ends for the mean.
+__device__ SetStat set_stat(const double *__restrict__ e, int n, int method, int n_trim, double *scratch, int n2,
+                            double *s_red) {
+  SetStat r;
+  const double *src = e;
+  int lo = 0, hi = n;          // mean over sorted[lo:hi]
+  int sd_lo = 0, sd_hi = n;    // std over [sd_lo:sd_hi]
+  bool empty_mean = false;
+  if (n_trim != 0 && method != FL_FIT_WELCH) {
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) scratch[i] = i < n ? e[i] : __longlong_as_double(0x7ff0000000000000LL);
+    __syncthreads();
+    block_bitonic_sort(scratch, n2);
+    src = scratch;
+    if (method == FL_FIT_YUEN) {
+      const int t = min(n_trim, (n - 1) / 2);
+      lo = t;
+      hi = n - t;
+      if (t == 0) empty_mean = true;  // python: energy_scores[0:-0] is the empty list
+    } else {
+      lo = min(n_trim, n);
+      if (method == FL_FIT_TRIM_LEFT_M_SD) sd_lo = lo;
+    }
+  }
+  const int cnt = hi - lo;
+  double acc = 0.0;
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) acc += src[i];
+  const double total = block_sum(acc, s_red);
+  r.mean = (cnt <= 0 || empty_mean) ? __longlong_as_double(0x7ff8000000000000LL) : total / (double)cnt;
+  // np.std(ddof=1): mean of the std window, then sum of squared deviations / (N-1)
+  const int scnt = sd_hi - sd_lo;
+  double a2 = 0.0;
+  for (int i = sd_lo + threadIdx.x; i < sd_hi; i += blockDim.x) a2 += src[i];
+  const double smean = block_sum(a2, s_red) / (double)scnt;
+  double q = 0.0;
+  for (int i = sd_lo + threadIdx.x; i < sd_hi; i += blockDim.x) {
+    const double d = src[i] - smean;
+    q += d * d;
+  }
+  const double ss = block_sum(q, s_red);
+  double sd = sqrt(ss / (double)(scnt - 1));
+  if (!(sd > 1.0)) sd = 1.0;  // max(1, stdev): python's max keeps 1 when stdev is nan (N == 1)
+  r.se = sd / sqrt((double)scnt);
+  return r;
+}
+
+__global__ void __launch_bounds__(256) fitness_kernel(const double *__restrict__ Epos, int n_pos, const double *__restrict__ Eneg,
+                                                      int n_neg, int method, int trim_pos, int trim_neg, double *scratch,
+                                                      int n2, double *__restrict__ out) {
+  __shared__ double s_red[32];
+  const int o = blockIdx.x;
+  double *sc = scratch + (size_t)o * n2;
+  const SetStat sp = set_stat(Epos + (size_t)o * n_pos, n_pos, method, trim_pos, sc, n2, s_red);
+  __syncthreads();
+  const SetStat sn = set_stat(Eneg + (size_t)o * n_neg, n_neg, method, trim_neg, sc, n2, s_red);
+  if (threadIdx.x == 0) {
+    out[o * 5 + 0] = (sp.mean - sn.mean) / sqrt(sp.se * sp.se + sn.se * sn.se);
+    out[o * 5 + 1] = sp.mean;
+    out[o * 5 + 2] = sp.se;
+    out[o * 5 + 3] = sn.mean;
+    out[o * 5 + 4] = sn.se;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: context, uploads, launch planning
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return FL_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    CK(cudaMalloc(&p, want));
+    cap = want;
+    return FL_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct SeqClass {
+  int len, begin, count;
+};
+
+struct SeqSet {
+  bool valid = false;
+  int n_seq = 0;
+  std::vector<SeqClass> classes;
+  DevBuf packed, unk, word_off, unk_off, order;
+  DevBuf E;  // energies [n_org][n_seq]
+  int E_n_org = 0;
+  bool E_valid = false;
+};
+
+struct Population {
+  bool valid = false;
+  int n_org = 0, n_rec_total = 0, max_rec = 0;
+  std::vector<int> rec_begin, sum_len, con_M, pool_len;
+  long long n_con = 0;
+  int max_pool = 0, min_sum_len = 0;
+  DevBuf d_rec_begin, d_rec_type, d_rec_len, d_rec_nb, d_rec_data, d_pool_begin, d_rec_pool, d_con_M, d_con_pool, d_sum_len;
+};
+
+struct fl_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  DevBuf tables, err_flag, con_begin, gaps, rsc, csc, fit_out, fit_scratch;
+  Population pop, scratch_pop;
+  SeqSet sets[FL_MAX_SETS + 1];  // the extra slot serves fl_calculate
+  long long launches = 0;
+};
+
+extern "C" const char *fl_last_error(void) { return g_last_error.c_str(); }
+extern "C" int fl_abi_version(void) { return 1; }
+
+extern "C" int fl_ctx_create(int device, const double *tables, long long n_tables, fl_ctx **out) {
+  if (!out || !tables) return fail(FL_E_ARG, "fl_ctx_create: null argument");
+  if (n_tables != FL_N_TABLE_DOUBLES) return fail(FL_E_ARG, "fl_ctx_create: expected %d table doubles, got %lld", FL_N_TABLE_DOUBLES, n_tables);
+  int count = 0;
+  CK(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return fail(FL_E_ARG, "fl_ctx_create: device %d not present (%d devices)", device, count);
+  CK(cudaSetDevice(device));
+  fl_ctx *ctx = new fl_ctx();
+  ctx->device = device;
+  cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete ctx;
+    return fail(FL_E_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+  }
+  int rc = ctx->tables.ensure(sizeof(double) * FL_N_TABLE_DOUBLES);
+  if (rc == FL_OK) rc = ctx->err_flag.ensure(sizeof(int));
+  if (rc != FL_OK) {
+    delete ctx;
+    return rc;
+  }
+  CK(cudaMemcpyAsync(ctx->tables.p, tables, sizeof(double) * FL_N_TABLE_DOUBLES, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(ctx->err_flag.p, 0, sizeof(int), ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaFuncSetAttribute(place_exact_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+  CK(cudaFuncSetAttribute(place_exact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+  *out = ctx;
+  return FL_OK;
+}
+
+static void release_pop(Population &p) {
+  DevBuf *bufs[] = {&p.d_rec_begin, &p.d_rec_type, &p.d_rec_len, &p.d_rec_nb, &p.d_rec_data,
+                    &p.d_pool_begin, &p.d_rec_pool, &p.d_con_M, &p.d_con_pool, &p.d_sum_len};
+  for (DevBuf *b : bufs) b->release();
+}
+
+extern "C" int fl_ctx_destroy(fl_ctx *ctx) {
+  if (!ctx) return FL_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (SeqSet &s : ctx->sets) {
+    s.packed.release(); s.unk.release(); s.word_off.release(); s.unk_off.release(); s.order.release(); s.E.release();
+  }
+  release_pop(ctx->pop);
+  release_pop(ctx->scratch_pop);
+  DevBuf *bufs[] = {&ctx->tables, &ctx->err_flag, &ctx->con_begin, &ctx->gaps, &ctx->rsc, &ctx->csc, &ctx->fit_out, &ctx->fit_scratch};
+  for (DevBuf *b : bufs) b->release();
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return FL_OK;
+}
+
+extern "C" void *fl_ctx_stream(fl_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" long long fl_launch_count(fl_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+static int check_device_errors(fl_ctx *ctx) {
+  int flag = 0;
+  CK(cudaMemcpyAsync(&flag, ctx->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (flag) {
+    CK(cudaMemsetAsync(ctx->err_flag.p, 0, sizeof(int), ctx->stream));
+    if (flag & ERR_NAN_NULL)
+      return fail(FL_E_NAN_NULL, "a shape score fell into a null-model bin whose frequency is NaN (the reference exits here, recognizer.c:258-262)");
+  }
+  return FL_OK;
+}
+
+extern "C" int fl_sync(fl_ctx *ctx) {
+  if (!ctx) return fail(FL_E_ARG, "fl_sync: null context");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return check_device_errors(ctx);
+}
+
+static inline int base_code(char c) {
+  switch (c) {
+    case 'a': case 'A': return 0;
+    case 'g': case 'G': return 1;
+    case 'c': case 'C': return 2;
+    case 't': case 'T': return 3;
+    default: return -1;
+  }
+}
+
+static int upload_sequences(fl_ctx *ctx, SeqSet &set, const char *bytes, const long long *offsets, int n_seq) {
+  if (n_seq < 0 || (n_seq > 0 && (!bytes || !offsets))) return fail(FL_E_ARG, "fl_upload_sequences: bad arguments");
+  std::vector<int> len(n_seq), word_off(n_seq), unk_off(n_seq), order(n_seq);
+  long long words = 0, uwords = 0;
+  for (int s = 0; s < n_seq; ++s) {
+    const long long l = offsets[s + 1] - offsets[s];
+    if (l < 0 || l > 100000000) return fail(FL_E_ARG, "fl_upload_sequences: sequence %d has length %lld", s, l);
+    len[s] = (int)l;
+    word_off[s] = (int)words;
+    unk_off[s] = (int)uwords;
+    words += (l + 15) / 16;
+    uwords += (l + 31) / 32;
+    if (words > 0x7fffffffLL) return fail(FL_E_ARG, "fl_upload_sequences: set too large");
+    order[s] = s;
+  }
+  std::vector<unsigned> packed((size_t)words + 1, 0u), unk((size_t)uwords + 1, 0u);
+  for (int s = 0; s < n_seq; ++s) {
+    const char *b = bytes + offsets[s];
+    unsigned *pw = packed.data() + word_off[s];
+    unsigned *uw = unk.data() + unk_off[s];
+    for (int i = 0; i < len[s]; ++i) {
+      const int c = base_code(b[i]);
+      if (c < 0) uw[i >> 5] |= 1u << (i & 31);
+      else pw[i >> 4] |= (unsigned)c << (2 * (i & 15));
+    }
+  }
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return len[a] < len[b]; });
+  set.classes.clear();
+  for (int i = 0; i < n_seq; ++i) {
+    const int l = len[order[i]];
+    if (set.classes.empty() || set.classes.back().len != l) set.classes.push_back({l, i, 0});
+    set.classes.back().count++;
+  }
+  set.n_seq = n_seq;
+  int rc;
+  if ((rc = set.packed.ensure(packed.size() * 4)) || (rc = set.unk.ensure(unk.size() * 4)) ||
+      (rc = set.word_off.ensure((size_t)n_seq * 4 + 4)) || (rc = set.unk_off.ensure((size_t)n_seq * 4 + 4)) ||
+      (rc = set.order.ensure((size_t)n_seq * 4 + 4)))
+    return rc;
+  CK(cudaMemcpyAsync(set.packed.p, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(set.unk.p, unk.data(), unk.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (n_seq) {
+    CK(cudaMemcpyAsync(set.word_off.p, word_off.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(set.unk_off.p, unk_off.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(set.order.p, order.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));  // the staging vectors die at return
+  set.valid = true;
+  set.E_valid = false;
+  return FL_OK;
+}
+
+extern "C" int fl_upload_sequences(fl_ctx *ctx, int set_id, const char *bytes, const long long *offsets, int n_seq) {
+  if (!ctx) return fail(FL_E_ARG, "fl_upload_sequences: null context");
+  if (set_id < 0 || set_id >= FL_MAX_SETS) return fail(FL_E_ARG, "fl_upload_sequences: set_id %d out of range [0,%d)", set_id, FL_MAX_SETS);
+  CK(cudaSetDevice(ctx->device));
+  return upload_sequences(ctx, ctx->sets[set_id], bytes, offsets, n_seq);
+}
+
+extern "C" int fl_sequence_classes(fl_ctx *ctx, int set_id, int *n_classes, int *class_len) {
+  if (!ctx || set_id < 0 || set_id >= FL_MAX_SETS || !ctx->sets[set_id].valid) return fail(FL_E_STATE, "fl_sequence_classes: no such set");
+  const SeqSet &s = ctx->sets[set_id];
+  if (n_classes) *n_classes = (int)s.classes.size();
+  if (class_len)
+    for (size_t i = 0; i < s.classes.size(); ++i) class_len[i] = s.classes[i].len;
+  return FL_OK;
+}
+
+static int upload_population(fl_ctx *ctx, Population &P, const fl_population *pop) {
+  if (!pop || pop->n_org < 0) return fail(FL_E_ARG, "fl_upload_population: bad population");
+  const int n_org = pop->n_org;
+  P.valid = false;
+  P.n_org = n_org;
+  P.n_rec_total = pop->n_rec_total;
+  P.rec_begin.assign(pop->rec_begin, pop->rec_begin + n_org + 1);
+  P.sum_len.assign(n_org, 0);
+  P.con_M.assign(pop->con_M, pop->con_M + n_org);
+  P.pool_len.assign(n_org, 0);
+  P.max_rec = 0;
+  P.max_pool = 0;
+  P.min_sum_len = 0x7fffffff;
+  P.n_con = pop->n_con;
+  if (n_org && (P.rec_begin[0] != 0 || P.rec_begin[n_org] != pop->n_rec_total)) return fail(FL_E_ARG, "fl_upload_population: rec_begin does not cover n_rec_total");
+  for (int o = 0; o < n_org; ++o) {
+    const int rb = P.rec_begin[o], n = P.rec_begin[o + 1] - rb;
+    if (n < 1 || n > FL_MAX_RECOGNIZERS) return fail(FL_E_ARG, "organism %d has %d recognizers (supported: 1..%d)", o, n, FL_MAX_RECOGNIZERS);
+    int sl = 0;
+    for (int i = 0; i < n; ++i) {
+      const char t = pop->rec_type[rb + i];
+      const int L = pop->rec_len[rb + i];
+      const bool is_p = (t == 'p' || t == 'P');
+      const bool is_s = (t == 'm' || t == 'M' || t == 't' || t == 'T' || t == 'r' || t == 'R' || t == 'h' || t == 'H');
+      if (!is_p && !is_s) return fail(FL_E_ARG, "organism %d recognizer %d: unknown type '%c'", o, i, t);
+      if (L < 1 || (is_s && L < 5)) return fail(FL_E_ARG, "organism %d recognizer %d: length %d not allowed for type '%c'", o, i, L, t);
+      if (is_s && pop->rec_nb[rb + i] < 2) return fail(FL_E_ARG, "organism %d recognizer %d: shape model needs >= 2 bin edges", o, i);
+      const long long need = is_p ? 4LL * L : 3LL * pop->rec_nb[rb + i] - 2;
+      const long long off = pop->rec_data[rb + i];
+      if (off < pop->pool_begin[o] || off + need > pop->pool_begin[o + 1]) return fail(FL_E_ARG, "organism %d recognizer %d: data outside the organism's pool slice", o, i);
+      sl += L;
+    }
+    P.sum_len[o] = sl;
+    P.pool_len[o] = (int)(pop->pool_begin[o + 1] - pop->pool_begin[o]);
+    P.max_rec = std::max(P.max_rec, n);
+    P.max_pool = std::max(P.max_pool, P.pool_len[o]);
+    P.min_sum_len = std::min(P.min_sum_len, sl);
+    if (n > 1 && P.con_M[o] < 1) return fail(FL_E_UNSUPPORTED, "organism %d: connectors without precomputed tables (legacy branch connector.c:70-72) are not supported", o);
+  }
+  int rc;
+  const size_t nr = (size_t)pop->n_rec_total;
+  if ((rc = P.d_rec_begin.ensure((n_org + 1) * 4)) || (rc = P.d_rec_type.ensure(nr + 4)) || (rc = P.d_rec_len.ensure(nr * 4 + 4)) ||
+      (rc = P.d_rec_nb.ensure(nr * 4 + 4)) || (rc = P.d_rec_data.ensure(nr * 8 + 8)) || (rc = P.d_pool_begin.ensure((n_org + 1) * 8)) ||
+      (rc = P.d_rec_pool.ensure((size_t)pop->n_pool * 8 + 8)) || (rc = P.d_con_M.ensure((size_t)n_org * 4 + 4)) ||
+      (rc = P.d_con_pool.ensure((size_t)pop->n_con * 8 + 8)) || (rc = P.d_sum_len.ensure((size_t)n_org * 4 + 4)))
+    return rc;
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(P.d_rec_begin.p, pop->rec_begin, (n_org + 1) * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(P.d_rec_type.p, pop->rec_type, nr, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(P.d_rec_len.p, pop->rec_len, nr * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(P.d_rec_nb.p, pop->rec_nb, nr * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(P.d_rec_data.p, pop->rec_data, nr * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(P.d_pool_begin.p, pop->pool_begin, (n_org + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (pop->n_pool) CK(cudaMemcpyAsync(P.d_rec_pool.p, pop->rec_pool, (size_t)pop->n_pool * 8, cudaMemcpyHostToDevice, st));
+  if (n_org) CK(cudaMemcpyAsync(P.d_con_M.p, pop->con_M, (size_t)n_org * 4, cudaMemcpyHostToDevice, st));
+  if (pop->n_con) CK(cudaMemcpyAsync(P.d_con_pool.p, pop->con_pool, (size_t)pop->n_con * 8, cudaMemcpyHostToDevice, st));
+  if (n_org) CK(cudaMemcpyAsync(P.d_sum_len.p, P.sum_len.data(), (size_t)n_org * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));  // caller may free its arrays as soon as we return
+  P.valid = true;
+  return FL_OK;
+}
+
+extern "C" int fl_upload_population(fl_ctx *ctx, const fl_population *pop) {
+  if (!ctx) return fail(FL_E_ARG, "fl_upload_population: null context");
+  CK(cudaSetDevice(ctx->device));
+  for (int s = 0; s < FL_MAX_SETS; ++s) ctx->sets[s].E_valid = false;
+  return upload_population(ctx, ctx->pop, pop);
+}
+
+static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long *con_begin, int flags, double *energies,
+                       int *gaps, double *rec_scores, double *con_scores) {
+  if (!P.valid) return fail(FL_E_STATE, "fl_place_batch: no population uploaded");
+  if (!set.valid) return fail(FL_E_STATE, "fl_place_batch: sequence set not uploaded");
+  const bool trace = (flags & FL_WANT_TRACE) != 0;
+  if (!trace && (gaps || rec_scores || con_scores)) return fail(FL_E_ARG, "fl_place_batch: gaps/scores need FL_WANT_TRACE");
+  const int n_org = P.n_org, n_seq = set.n_seq, n_cls = (int)set.classes.size();
+  set.E_valid = false;
+  if (n_org == 0 || n_seq == 0) {
+    set.E_n_org = n_org;
+    set.E_valid = true;
+    return FL_OK;
+  }
+  if (!con_begin) return fail(FL_E_ARG, "fl_place_batch: con_begin is required");
+  // ---- admissibility (organism_object.py:1279, organism.c:262,336, _constants.h:11) ---------------
+  for (int c = 0; c < n_cls; ++c) {
+    const int S = set.classes[c].len;
+    for (int o = 0; o < n_org; ++o) {
+      const int n = P.rec_begin[o + 1] - P.rec_begin[o];
+      if (P.sum_len[o] > S)
+        return fail(FL_E_TOO_LARGE, "organism %d (sum of recognizer lengths %d) is too large to be placed on a sequence of length %d", o, P.sum_len[o], S);
+      if (n > 1) {
+        if (S - P.sum_len[o] > P.con_M[o] - 1)
+          return fail(FL_E_UNSUPPORTED, "organism %d: gap tables cover %d lengths but a sequence of length %d needs %d (legacy non-precomputed branch, organism.c:336-338)",
+                      o, P.con_M[o], S, S - P.sum_len[o] + 1);
+        const long long cb = con_begin[(size_t)c * n_org + o];
+        if (cb < 0 || cb + (long long)(n - 1) * (2LL * P.con_M[o] + 2) > P.n_con)
+          return fail(FL_E_ARG, "con_begin[class %d][organism %d] points outside con_pool", c, o);
+      }
+      if (S - P.sum_len[o] + n > 10000) return fail(FL_E_UNSUPPORTED, "effective length %d exceeds DEN_EXPANSION (10000 entries, _constants.h:11)", S - P.sum_len[o] + n);
+    }
+  }
+  int rc;
+  if ((rc = set.E.ensure((size_t)n_org * n_seq * 8))) return rc;
+  if ((rc = ctx->con_begin.ensure((size_t)n_cls * n_org * 8))) return rc;
+  if (trace) {
+    const size_t cells = (size_t)n_org * n_seq * P.max_rec;
+    if ((rc = ctx->gaps.ensure(cells * 4)) || (rc = ctx->rsc.ensure(cells * 8)) || (rc = ctx->csc.ensure(cells * 8))) return rc;
+    CK(cudaMemsetAsync(ctx->gaps.p, 0, cells * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->rsc.p, 0, cells * 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->csc.p, 0, cells * 8, ctx->stream));
+  }
+  CK(cudaMemcpyAsync(ctx->con_begin.p, con_begin, (size_t)n_cls * n_org * 8, cudaMemcpyHostToDevice, ctx->stream));
+
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+
+  for (int c = 0; c < n_cls; ++c) {
+    const SeqClass &cl = set.classes[c];
+    PlaceParams pp;
+    pp.rec_begin = P.d_rec_begin.as<int>();
+    pp.rec_type = P.d_rec_type.as<char>();
+    pp.rec_len = P.d_rec_len.as<int>();
+    pp.rec_nb = P.d_rec_nb.as<int>();
+    pp.rec_data = P.d_rec_data.as<long long>();
+    pp.pool_begin = P.d_pool_begin.as<long long>();
+    pp.rec_pool = P.d_rec_pool.as<double>();
+    pp.con_M = P.d_con_M.as<int>();
+    pp.con_pool = P.d_con_pool.as<double>();
+    pp.con_begin = ctx->con_begin.as<long long>() + (size_t)c * n_org;
+    pp.sum_len = P.d_sum_len.as<int>();
+    pp.packed = set.packed.as<unsigned>();
+    pp.unk = set.unk.as<unsigned>();
+    pp.word_off = set.word_off.as<int>();
+    pp.unk_off = set.unk_off.as<int>();
+    pp.order = set.order.as<int>();
+    pp.class_begin = cl.begin;
+    pp.class_count = cl.count;
+    pp.S = cl.len;
+    pp.n_seq_total = n_seq;
+    pp.tables = ctx->tables.as<double>();
+    pp.E = set.E.as<double>();
+    pp.gaps = ctx->gaps.as<int>();
+    pp.rsc = ctx->rsc.as<double>();
+    pp.csc = ctx->csc.as<double>();
+    pp.max_rec = P.max_rec;
+    pp.err_flag = ctx->err_flag.as<int>();
+
+    const int Pmax = cl.len - P.min_sum_len + 1;
+    pp.pool_stride = (P.max_pool + 1) & ~1;
+    pp.g_stride = kPadLo + Pmax + kPadHi;
+    pp.row_stride = (Pmax + 3) & ~3;
+    pp.code_stride = (cl.len + 15) & ~15;
+    pp.nrows = trace ? P.max_rec : std::min(2, P.max_rec);
+    int nwarps = 8;
+    size_t smem = 0;
+    for (;; nwarps >>= 1) {
+      smem = 8ull * ((size_t)pp.pool_stride + (size_t)(P.max_rec - 1) * pp.g_stride + (size_t)nwarps * pp.nrows * pp.row_stride) +
+             sizeof(RecDesc) * P.max_rec + (size_t)nwarps * pp.code_stride;
+      // prefer configurations that leave room for >= 2 resident CTAs unless that costs warps
+      if (smem <= (size_t)kMaxSmem && (nwarps <= 4 || smem <= (size_t)kMaxSmem / 2)) break;
+      if (nwarps == 1) break;
+    }
+    if (smem > (size_t)kMaxSmem)
+      return fail(FL_E_UNSUPPORTED, "placement of %d offsets x %d recognizers needs %zu bytes of shared memory (limit %d)", Pmax, P.max_rec, smem, kMaxSmem);
+    // chunking: enough CTAs to fill the machine a few times over, at least one sequence per warp
+    const long long pairs = (long long)n_org * cl.count;
+    long long target_ctas = (long long)n_sm * 16;
+    int spc = (int)std::max<long long>(nwarps, (pairs + target_ctas - 1) / target_ctas);
+    spc = std::min(spc, std::max(nwarps, 64));
+    spc = ((spc + nwarps - 1) / nwarps) * nwarps;
+    pp.seqs_per_cta = spc;
+    pp.chunks = (cl.count + spc - 1) / spc;
+    const long long grid = (long long)n_org * pp.chunks;
+    if (grid > 0x7fffffffLL) return fail(FL_E_UNSUPPORTED, "grid too large");
+    if (trace)
+      place_exact_kernel<true><<<(unsigned)grid, nwarps * 32, smem, ctx->stream>>>(pp);
+    else
+      place_exact_kernel<false><<<(unsigned)grid, nwarps * 32, smem, ctx->stream>>>(pp);
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
+  set.E_n_org = n_org;
+  set.E_valid = true;
+  if (energies || gaps || rec_scores || con_scores) {
+    const size_t pairs = (size_t)n_org * n_seq;
+    if (energies) CK(cudaMemcpyAsync(energies, set.E.p, pairs * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (gaps) CK(cudaMemcpyAsync(gaps, ctx->gaps.p, pairs * P.max_rec * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rec_scores) CK(cudaMemcpyAsync(rec_scores, ctx->rsc.p, pairs * P.max_rec * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (con_scores) CK(cudaMemcpyAsync(con_scores, ctx->csc.p, pairs * P.max_rec * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    return check_device_errors(ctx);
+  }
+  return FL_OK;
+}
+
+extern "C" int fl_place_batch(fl_ctx *ctx, int set_id, const long long *con_begin, int flags, double *energies, int *gaps,
+                              double *rec_scores, double *con_scores) {
+  if (!ctx) return fail(FL_E_ARG, "fl_place_batch: null context");
+  if (set_id < 0 || set_id >= FL_MAX_SETS) return fail(FL_E_ARG, "fl_place_batch: set_id %d out of range", set_id);
+  CK(cudaSetDevice(ctx->device));
+  return place_batch(ctx, ctx->pop, ctx->sets[set_id], con_begin, flags, energies, gaps, rec_scores, con_scores);
+}
+
+extern "C" int fl_fitness(fl_ctx *ctx, int pos_set, int neg_set, int method, double gamma, double *out) {
+  if (!ctx || !out) return fail(FL_E_ARG, "fl_fitness: null argument");
+  if (pos_set < 0 || pos_set >= FL_MAX_SETS || neg_set < 0 || neg_set >= FL_MAX_SETS) return fail(FL_E_ARG, "fl_fitness: set id out of range");
+  if (method < FL_FIT_WELCH || method > FL_FIT_TRIM_LEFT_M_SD) return fail(FL_E_ARG, "fl_fitness: unknown method %d", method);
+  CK(cudaSetDevice(ctx->device));
+  SeqSet &sp = ctx->sets[pos_set], &sn = ctx->sets[neg_set];
+  if (!sp.E_valid || !sn.E_valid || sp.E_n_org != sn.E_n_org) return fail(FL_E_STATE, "fl_fitness: energies of both sets must be computed (fl_place_batch) for the current population");
+  const int n_org = sp.E_n_org;
+  if (n_org == 0) return FL_OK;
+  if (sp.n_seq < 1 || sn.n_seq < 1) return fail(FL_E_ARG, "fl_fitness: empty sequence set");
+  // n_to_trim = round(gamma * N): python rounds half to even (organism_object.py:892), as nearbyint does
+  const int trim_p = (int)std::nearbyint(gamma * (double)sp.n_seq);
+  const int trim_n = (int)std::nearbyint(gamma * (double)sn.n_seq);
+  int n2 = 1;
+  while (n2 < std::max(sp.n_seq, sn.n_seq)) n2 <<= 1;
+  const bool need_sort = method != FL_FIT_WELCH && (trim_p != 0 || trim_n != 0);
+  int rc;
+  if ((rc = ctx->fit_out.ensure((size_t)n_org * 5 * 8))) return rc;
+  if (need_sort && (rc = ctx->fit_scratch.ensure((size_t)n_org * n2 * 8))) return rc;
+  fitness_kernel<<<n_org, 256, 0, ctx->stream>>>(sp.E.as<double>(), sp.n_seq, sn.E.as<double>(), sn.n_seq, method, trim_p, trim_n,
+                                                 ctx->fit_scratch.as<double>(), n2, ctx->fit_out.as<double>());
+  CK(cudaGetLastError());
+  ctx->launches++;
+  CK(cudaMemcpyAsync(out, ctx->fit_out.p, (size_t)n_org * 5 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  return check_device_errors(ctx);
+}
+
+extern "C" int fl_calculate(fl_ctx *ctx, const char *sequence, int seq_len, const char *rec_types, int n_rec,
+                            const double *rec_matrices, const int *rec_lengths, const double *con_matrices,
+                            long long n_con_doubles, double *rec_scores, double *con_scores, int *con_lengths, int max_length,
+                            const double *bin_freqs, const double *bin_edges, const int *num_bins) {
+  if (!ctx || !sequence || !rec_types || !rec_lengths || !rec_scores || !con_lengths) return fail(FL_E_ARG, "fl_calculate: null argument");
+  if (n_rec < 1 || n_rec > FL_MAX_RECOGNIZERS) return fail(FL_E_ARG, "fl_calculate: %d recognizers (supported 1..%d)", n_rec, FL_MAX_RECOGNIZERS);
+  if (n_rec > 1 && !con_scores) return fail(FL_E_ARG, "fl_calculate: con_scores is null");
+  CK(cudaSetDevice(ctx->device));
+  // _interface.c:131-136: 2 doubles per connector means "not precomputed"
+  if (n_rec > 1 && n_con_doubles == 2LL * (n_rec - 1))
+    return fail(FL_E_UNSUPPORTED, "connectors without precomputed pdf/cdf tables (PRECOMPUTE=false, connector.c:70-72) are not supported");
+  const int M = max_length + 1;
+  if (n_rec > 1 && (M < 1 || n_con_doubles != (long long)(n_rec - 1) * (2LL * M + 2)))
+    return fail(FL_E_ARG, "fl_calculate: con_matrices has %lld doubles, expected %lld for max_length %d", n_con_doubles, (long long)(n_rec - 1) * (2LL * M + 2), max_length);
+  // build a one-organism population
+  std::vector<double> pool;
+  std::vector<long long> rec_data(n_rec);
+  std::vector<int> rec_nb(n_rec, 0);
+  long long m_off = 0, a_off = 0, e_off = 0;
+  int shape_i = 0;
+  for (int i = 0; i < n_rec; ++i) {
+    rec_data[i] = (long long)pool.size();
+    const int L = rec_lengths[i];
+    if (L < 1) return fail(FL_E_ARG, "fl_calculate: recognizer %d has length %d", i, L);
+    if (rec_types[i] == 'p' || rec_types[i] == 'P') {
+      if (!rec_matrices) return fail(FL_E_ARG, "fl_calculate: rec_matrices is null");
+      pool.insert(pool.end(), rec_matrices + m_off, rec_matrices + m_off + 4LL * L);
+      m_off += 4LL * L;
+    } else {
+      if (!bin_freqs || !bin_edges || !num_bins) return fail(FL_E_ARG, "fl_calculate: shape model arrays are null");
+      const int nb = num_bins[shape_i];
+      if (nb < 2) return fail(FL_E_ARG, "fl_calculate: shape recognizer %d has %d bin edges", i, nb);
+      rec_nb[i] = nb;
+      pool.insert(pool.end(), bin_freqs + a_off, bin_freqs + a_off + 2LL * (nb - 1));  // null ++ alt (organism.c:159-172)
+      pool.insert(pool.end(), bin_edges + e_off, bin_edges + e_off + nb);
+      a_off += 2LL * (nb - 1);
+      e_off += nb;
+      ++shape_i;
+    }
+  }
+  const int rec_begin[2] = {0, n_rec};
+  const long long pool_begin[2] = {0, (long long)pool.size()};
+  const int con_M = n_rec > 1 ? M : 0;
+  fl_population pop;
+  pop.n_org = 1;
+  pop.n_rec_total = n_rec;
+  pop.rec_begin = rec_begin;
+  pop.rec_type = rec_types;
+  pop.rec_len = rec_lengths;
+  pop.rec_nb = rec_nb.data();
+  pop.rec_data = rec_data.data();
+  pop.pool_begin = pool_begin;
+  pop.rec_pool = pool.data();
+  pop.n_pool = (long long)pool.size();
+  pop.con_M = &con_M;
+  pop.con_pool = con_matrices;
+  pop.n_con = n_rec > 1 ? n_con_doubles : 0;
+  int rc = upload_population(ctx, ctx->scratch_pop, &pop);
+  if (rc) return rc;
+  SeqSet &set = ctx->sets[FL_MAX_SETS];
+  const long long offs[2] = {0, seq_len};
+  if ((rc = upload_sequences(ctx, set, sequence, offs, 1))) return rc;
+  const long long con_begin = 0;
+  double energy = 0.0;
+  std::vector<int> gaps(n_rec);
+  std::vector<double> rsc(n_rec), csc(n_rec);
+  rc = place_batch(ctx, ctx->scratch_pop, set, &con_begin, FL_WANT_TRACE, &energy, gaps.data(), rsc.data(), csc.data());
+  if (rc) return rc;
+  for (int i = 0; i < n_rec; ++i) {
+    rec_scores[i] = rsc[i];
+    con_lengths[i] = gaps[i];
+    if (i + 1 < n_rec) con_scores[i] = csc[i];
+  }
+  rec_scores[n_rec] = energy;
+  return FL_OK;
+}

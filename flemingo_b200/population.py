@@ -1,0 +1,223 @@
+"""Host-side packer: a list of organisms -> the struct-of-arrays `fl_population` of include/flemingo_b200.h.
+
+An "organism" here is anything that carries the flat arrays `OrganismObject.flatten()` produces
+(reference: src/objects/organism_object.py:1362-1504): `recognizer_types`, `recognizers_flat`,
+`recognizer_lengths`, `recognizer_models`, `recognizer_bin_edges`, `recognizer_bin_nums`,
+`connectors_scores_flat`, `sum_recognizer_lengths`, and `connectors` (objects with `_mu`, `_sigma`,
+`pseudo_count`, `max_seq_length`).  Both flemingo_b200.objects.OrganismObject and the reference's own class
+qualify, which is what makes the GPU path a drop-in.
+
+The packer also owns the one piece of per-call host arithmetic of `get_placement`: the connector rescale
+(organism_object.py:1312-1329 -> ConnectorObject.adjust_scores, connector_object.py:454-487).  It depends on
+(organism, connector, sequence length) only, so it is evaluated once per length class and appended to the
+connector pool as a variant table.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+SHAPE_TYPES = "mtrh"
+
+
+def _g(x, mu, sigma):
+    # connector_object.py:15-16
+    return -(1 / 2) * ((x - mu) / sigma) ** 2
+
+
+def rescale_connector_block(block: np.ndarray, mu: float, sigma: float, pseudo_count: float, M: int,
+                            sequence_length: int, sum_recognizer_lengths: int) -> None:
+    """In-place restatement of ConnectorObject.adjust_scores (connector_object.py:454-487).
+
+    `block` is the connector's [pdf[0..M) ++ cdf[0..M)] slice (the reference passes `c_scores[offset:]`).
+    Natural logs on purpose: that is what the reference writes (unlike the log2 tables of :175-206).
+    sigma == 0 raises ZeroDivisionError exactly as the reference does.
+    """
+    sigma = min(sigma, 1E-100)
+    top = sequence_length - sum_recognizer_lengths
+    g_curr = _g(top, mu, sigma)
+    h_curr = 1
+    weights = [1 + pseudo_count]
+    total = weights[0]
+    for i in range(top - 1, -1, -1):
+        g_next = _g(i, mu, sigma)
+        h_next = h_curr * math.exp(g_next - g_curr)
+        weights.append(h_next + pseudo_count)
+        total += h_next + pseudo_count
+        g_curr = g_next
+        h_curr = h_next
+    probs = [h / total for h in reversed(weights)]
+    running = 0.0
+    for i, p in enumerate(probs):
+        running += p
+        block[i] = np.log(p)
+        block[M + i] = np.log(running)
+
+
+@dataclass
+class PackedPopulation:
+    """Struct-of-arrays population (host numpy arrays, C-contiguous, dtypes as in fl_population)."""
+    n_org: int
+    rec_begin: np.ndarray     # int32 [n_org+1]
+    rec_type: np.ndarray      # uint8 [n_rec_total]
+    rec_len: np.ndarray       # int32 [n_rec_total]
+    rec_nb: np.ndarray        # int32 [n_rec_total]
+    rec_data: np.ndarray      # int64 [n_rec_total]
+    pool_begin: np.ndarray    # int64 [n_org+1]
+    rec_pool: np.ndarray      # float64
+    con_M: np.ndarray         # int32 [n_org]
+    con_pool: np.ndarray      # float64, base tables followed by rescaled variants
+    con_base: np.ndarray      # int64 [n_org] offset of each organism's own tables in con_pool
+    sum_len: np.ndarray       # int32 [n_org]
+    pseudo_count: np.ndarray  # float64 [n_org] connector pseudo count
+    ids: list = field(default_factory=list)
+    # (organism index, sequence length) -> offset of the rescaled variant in con_pool
+    variants: dict = field(default_factory=dict)
+    n_base_con: int = 0
+    uploaded_con_size: int = -1
+
+    @property
+    def n_rec(self) -> np.ndarray:
+        return np.diff(self.rec_begin)
+
+    @property
+    def max_rec(self) -> int:
+        return int(self.n_rec.max()) if self.n_org else 0
+
+    def con_begin_for_lengths(self, lengths) -> np.ndarray:
+        """con_begin[class][organism] for the given class lengths; creates rescaled variants on demand.
+
+        Trigger, per connector (organism_object.py:1317-1329): float(S) + 0.5 < mu and
+        pdf[S - sum_len] <= ln(1e-15).
+        """
+        lengths = [int(x) for x in lengths]
+        out = np.empty((len(lengths), self.n_org), dtype=np.int64)
+        n_rec = self.n_rec
+        multi = np.nonzero(n_rec > 1)[0]
+        threshold = np.log(1E-15)
+        extra = []
+        extra_off = self.con_pool.size
+        for ci, S in enumerate(lengths):
+            out[ci, :] = self.con_base
+            for o in multi:
+                key = (int(o), S)
+                if key in self.variants:
+                    out[ci, o] = self.variants[key]
+                    continue
+                M = int(self.con_M[o])
+                stride = 2 * M + 2
+                base = int(self.con_base[o])
+                nc = int(n_rec[o]) - 1
+                idx = S - int(self.sum_len[o])
+                if idx < 0 or idx >= M:
+                    continue  # inadmissible pair; the library reports it
+                mus = self.con_pool[base:base + nc * stride:stride]
+                if not np.any(float(S) + 0.5 < mus):
+                    continue
+                block = None
+                for c in range(nc):
+                    mu = float(self.con_pool[base + c * stride])
+                    if float(S) + 0.5 < mu and self.con_pool[base + c * stride + 2 + idx] <= threshold:
+                        if block is None:
+                            block = self.con_pool[base:base + nc * stride].copy()
+                        sigma = float(block[c * stride + 1])
+                        rescale_connector_block(block[c * stride + 2:(c + 1) * stride], mu, sigma,
+                                                float(self.pseudo_count[o]), M, S, int(self.sum_len[o]))
+                if block is not None:
+                    self.variants[key] = extra_off
+                    out[ci, o] = extra_off
+                    extra.append(block)
+                    extra_off += block.size
+        if extra:
+            self.con_pool = np.concatenate([self.con_pool] + extra)
+        return out
+
+
+def pack_population(organisms) -> PackedPopulation:
+    """Packs organisms (flattened, see module docstring) into one PackedPopulation."""
+    n_org = len(organisms)
+    rec_begin = np.zeros(n_org + 1, dtype=np.int32)
+    pool_begin = np.zeros(n_org + 1, dtype=np.int64)
+    con_base = np.zeros(n_org, dtype=np.int64)
+    con_M = np.zeros(n_org, dtype=np.int32)
+    sum_len = np.zeros(n_org, dtype=np.int32)
+    pcs = np.zeros(n_org, dtype=np.float64)
+    types, lens, nbs, datas, pool_parts, con_parts, ids = [], [], [], [], [], [], []
+    pool_off = 0
+    con_off = 0
+    for o, org in enumerate(organisms):
+        rtypes = org.recognizer_types
+        n = len(rtypes)
+        if n < 1:
+            raise ValueError(f"organism {getattr(org, '_id', o)} has no recognizers")
+        rlens = np.asarray(org.recognizer_lengths, dtype=np.int32)
+        if rlens.size != n:
+            raise ValueError("organism is not flattened: recognizer_lengths does not match recognizer_types")
+        pssm = np.ascontiguousarray(org.recognizers_flat, dtype=np.float64)
+        models = np.ascontiguousarray(org.recognizer_models, dtype=np.float64)
+        edges = np.ascontiguousarray(org.recognizer_bin_edges, dtype=np.float64)
+        bin_nums = np.asarray(org.recognizer_bin_nums, dtype=np.int32)
+        m_off = a_off = e_off = shape_i = 0
+        org_parts = []
+        org_pool = 0
+        for i, t in enumerate(rtypes):
+            L = int(rlens[i])
+            datas.append(pool_off + org_pool)
+            if t in "pP":
+                org_parts.append(pssm[m_off:m_off + 4 * L])
+                if org_parts[-1].size != 4 * L:
+                    raise ValueError("recognizers_flat is shorter than the PSSM lengths require")
+                m_off += 4 * L
+                org_pool += 4 * L
+                nbs.append(0)
+            else:
+                nb = int(bin_nums[shape_i])
+                # parse_org (organism.c:159-185): null = models+a, alt = models+a+(nb-1), edges = edges+e
+                org_parts.append(models[a_off:a_off + 2 * (nb - 1)])
+                org_parts.append(edges[e_off:e_off + nb])
+                a_off += 2 * (nb - 1)
+                e_off += nb
+                org_pool += 3 * nb - 2
+                shape_i += 1
+                nbs.append(nb)
+            types.append(ord(t))
+            lens.append(L)
+        pool_parts.extend(org_parts)
+        pool_off += org_pool
+        rec_begin[o + 1] = rec_begin[o] + n
+        pool_begin[o + 1] = pool_off
+        sum_len[o] = int(rlens.sum())
+        con = np.ascontiguousarray(org.connectors_scores_flat, dtype=np.float64)
+        con_base[o] = con_off
+        if n > 1:
+            if con.size == 2 * (n - 1):
+                raise NotImplementedError(
+                    "organism.PRECOMPUTE=false (connectors without pdf/cdf tables) uses the reference's legacy "
+                    "float maths (connector.c:70-72, _aux.c:47-139); the GPU path requires precomputed tables")
+            M = int(org.connectors[0].max_seq_length)
+            if con.size != (n - 1) * (2 * M + 2):
+                raise ValueError("connectors_scores_flat does not match (n-1) * (2*max_seq_length + 2)")
+            con_M[o] = M
+            pcs[o] = float(org.connectors[0].pseudo_count)
+            con_parts.append(con)
+            con_off += con.size
+        ids.append(getattr(org, "_id", str(o)))
+    rec_pool = np.concatenate(pool_parts) if pool_parts else np.zeros(0)
+    con_pool = np.concatenate(con_parts) if con_parts else np.zeros(0)
+    return PackedPopulation(
+        n_org=n_org, rec_begin=rec_begin, rec_type=np.asarray(types, dtype=np.uint8),
+        rec_len=np.asarray(lens, dtype=np.int32), rec_nb=np.asarray(nbs, dtype=np.int32),
+        rec_data=np.asarray(datas, dtype=np.int64), pool_begin=pool_begin,
+        rec_pool=np.ascontiguousarray(rec_pool, dtype=np.float64), con_M=con_M,
+        con_pool=np.ascontiguousarray(con_pool, dtype=np.float64), con_base=con_base, sum_len=sum_len,
+        pseudo_count=pcs, ids=ids, n_base_con=int(con_pool.size))
+
+
+def placement_cost(packed: PackedPopulation, seq_len: int) -> np.ndarray:
+    """Relative cost of placing each organism on one sequence of length seq_len: (n-1) * P^2 DP cells
+    plus the score rows.  Used to balance organisms across GPUs."""
+    P = np.maximum(seq_len - packed.sum_len.astype(np.int64) + 1, 1)
+    n = packed.n_rec.astype(np.int64)
+    return (n - 1) * P * (P + 1) // 2 + P * packed.sum_len

@@ -1,0 +1,139 @@
+/*
+ * flemingo_b200.h -- C ABI of libflemingo_b200.so, the B200 (sm_100a) replacement for FLEMINGO's
+ * placement/fitness hot path.
+ *
+ * Every entry point cites the reference interface it replaces (paths relative to the FLEMINGO tree).
+ * Conventions:
+ *   - plain C types only; every pointer argument is HOST memory owned by the caller unless a name ends in
+ *     "_dev"; device memory is owned by the context;
+ *   - every function returns 0 (FL_OK) or a negative FL_E* code; the message is in fl_last_error()
+ *     (thread-local).  Nothing calls exit() and no C++ exception crosses the boundary (the reference calls
+ *     exit(1) on a NaN null-model bin, extensions/multiplacement/src/organism/recognizer.c:258-262);
+ *   - all device work of a context is issued on ONE stream (fl_ctx_stream); calls that return host data
+ *     synchronise that stream, the others are asynchronous until fl_sync();
+ *   - one context per process and device; contexts are not thread-safe (the reference holds the GIL for the
+ *     whole call, src/_interface.c:45-185).
+ */
+#ifndef FLEMINGO_B200_H
+#define FLEMINGO_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FL_OK 0
+#define FL_E_CUDA (-1)        /* a CUDA runtime call failed */
+#define FL_E_ARG (-2)         /* malformed argument */
+#define FL_E_TOO_LARGE (-3)   /* sum of recognizer lengths > sequence length:
+                                 organism.c:262 returns -1 -> RuntimeError at _interface.c:162-166;
+                                 organism_object.py:1279 raises ValueError first */
+#define FL_E_NAN_NULL (-4)    /* a NaN null-model bin was selected (reference: exit(1), recognizer.c:258-262) */
+#define FL_E_UNSUPPORTED (-5) /* input needs the legacy non-precomputed connector branch (connector.c:70-72,
+                                 organism.c:336-338), gap tables shorter than the sequence, eff_len > 10000
+                                 (reads past DEN_EXPANSION, _constants.h:11), or exceeds the shared-memory plan */
+#define FL_E_STATE (-6)       /* call order: missing population / sequence set / energies */
+
+#define FL_N_TABLE_DOUBLES 16144 /* MGW[1024] PROT[1024] ROLL[2048] HELT[2048] DEN_EXPANSION[10000], _constants.h:7-11 */
+#define FL_MAX_RECOGNIZERS 16    /* per organism; reference config default MAX_NUM_OF_RECOGNIZERS is 5 */
+#define FL_MAX_SETS 8
+
+/* flags of fl_place_batch */
+#define FL_WANT_TRACE 1   /* also produce start/gaps and per-node scores (organism.c:398-427) */
+
+/* fitness methods, src/objects/organism_object.py:848-936 */
+#define FL_FIT_WELCH 0
+#define FL_FIT_YUEN 1
+#define FL_FIT_TRIM_LEFT_M 2
+#define FL_FIT_TRIM_LEFT_M_SD 3
+
+typedef struct fl_ctx fl_ctx;
+
+/*
+ * A packed population: struct-of-arrays over organisms and their recognizers.  Built by the host from the
+ * per-organism flat arrays that OrganismObject.flatten() produces (organism_object.py:1362-1504).
+ */
+typedef struct fl_population {
+  int n_org;
+  int n_rec_total;
+  const int *rec_begin;        /* [n_org+1] first recognizer of organism o in the per-recognizer arrays */
+  const char *rec_type;        /* [n_rec_total] 'p','m','t','r','h' (shape_object.py:407-418) */
+  const int *rec_len;          /* [n_rec_total] recognizer length in bp */
+  const int *rec_nb;           /* [n_rec_total] number of bin EDGES of a shape recognizer (0 for 'p') */
+  const long long *rec_data;   /* [n_rec_total] offset into rec_pool: PSSM = 4*len doubles, column major
+                                  [col][A,G,C,T] (organism_object.py:1455-1458); shape = null[nb-1] ++
+                                  alt[nb-1] ++ edges[nb] (organism.c:159-185) */
+  const long long *pool_begin; /* [n_org+1] slice of rec_pool used by organism o */
+  const double *rec_pool;
+  long long n_pool;
+  const int *con_M;            /* [n_org] length M of each pdf / cdf block = ConnectorObject.max_seq_length
+                                  (the reference passes max_length = M-1, organism_object.py:1307) */
+  const double *con_pool;      /* connector tables: per organism (n_rec-1) blocks [mu, sigma, pdf[M], cdf[M]]
+                                  (organism_object.py:1490-1495); variants rescaled by adjust_scores
+                                  (connector_object.py:454-487) are appended by the host */
+  long long n_con;
+} fl_population;
+
+const char *fl_last_error(void);
+int fl_abi_version(void);
+
+/* Creates the context on `device` and uploads the data tables (_constants.h:7-11; tables.bin order). */
+int fl_ctx_create(int device, const double *tables, long long n_tables, fl_ctx **out);
+int fl_ctx_destroy(fl_ctx *ctx);
+/* The cudaStream_t all work of this context is issued on (for event timing by the caller). */
+void *fl_ctx_stream(fl_ctx *ctx);
+int fl_sync(fl_ctx *ctx);
+
+/*
+ * Uploads a DNA set (replaces the per-call `bytes(sequence, "ASCII")` of organism_object.py:1331).
+ * bytes = the sequences back to back, offsets[n_seq+1].  Bases are packed 2 bits each (A=0,G=1,C=2,T=3,
+ * case-insensitive, recognizer.c:143-163) plus a 1-bit "unknown byte" mask so that non-ACGT bytes keep
+ * the reference behaviour (no PSSM contribution; code 0 in a pentamer index).
+ * Sequences are grouped by length into classes (ascending length); n_classes/class_len report them.
+ */
+int fl_upload_sequences(fl_ctx *ctx, int set_id, const char *bytes, const long long *offsets, int n_seq);
+int fl_sequence_classes(fl_ctx *ctx, int set_id, int *n_classes, int *class_len /* [n_classes] or NULL */);
+
+/* Uploads the population (replaces parse_org, organism.c:112-211). */
+int fl_upload_population(fl_ctx *ctx, const fl_population *pop);
+
+/*
+ * Places every organism on every sequence of the set (replaces the loop of
+ * OrganismObject.get_binding_energies over get_placement, organism_object.py:958-966,1263-1357, i.e.
+ * n_org*n_seq calls of _multiplacement.calculate, _interface.c:45).
+ *   con_begin[class*n_org + o] = offset into con_pool of the connector tables organism o uses for
+ *                                sequences of that class (base tables, or an adjust_scores variant).
+ * Energies stay resident on the device for fl_fitness.  Host outputs may each be NULL:
+ *   energies[o*n_seq + s]                       (rec_scores[n] of calculate)
+ *   gaps[(o*n_seq+s)*max_rec + i]               (con_lengths of calculate: start, then gaps)
+ *   rec_scores / con_scores likewise            (max_rec = largest n_rec in the population)
+ * gaps/rec_scores/con_scores require FL_WANT_TRACE.
+ */
+int fl_place_batch(fl_ctx *ctx, int set_id, const long long *con_begin, int flags, double *energies, int *gaps,
+                   double *rec_scores, double *con_scores);
+
+/*
+ * Per-organism fitness statistic from the resident energies of two sets (replaces
+ * OrganismObject.get_M_and_SE_on_DNA_set + set_fitness, organism_object.py:848-956).
+ * out[o*5 + {0..4}] = fitness, M_pos, SE_pos, M_neg, SE_neg.
+ */
+int fl_fitness(fl_ctx *ctx, int pos_set, int neg_set, int method, double gamma, double *out);
+
+/*
+ * One placement with the exact argument list of _multiplacement.calculate (src/_interface.c:45-185,
+ * kwlist :49-52): sequence (+length), rec_types (+n_rec), rec_matrices, rec_lengths, con_matrices,
+ * rec_scores (out, n+1), con_scores (out, n-1), con_lengths (out, n), max_length, bin_freqs, bin_edges,
+ * num_bins.  n_con_doubles is the length of con_matrices (the reference reads it from the buffer shape,
+ * _interface.c:131).
+ */
+int fl_calculate(fl_ctx *ctx, const char *sequence, int seq_len, const char *rec_types, int n_rec,
+                 const double *rec_matrices, const int *rec_lengths, const double *con_matrices,
+                 long long n_con_doubles, double *rec_scores, double *con_scores, int *con_lengths, int max_length,
+                 const double *bin_freqs, const double *bin_edges, const int *num_bins);
+
+/* Counters for bench.py: kernels launched by this context since creation, and the last launch geometry. */
+long long fl_launch_count(fl_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLEMINGO_B200_H */

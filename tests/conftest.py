@@ -1,0 +1,48 @@
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+REPO = Path(__file__).resolve().parents[1]
+if str(REPO) not in sys.path:
+    sys.path.insert(0, str(REPO))
+
+GOLDEN = REPO / "tests" / "golden" / "golden_v1.json"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    with open(GOLDEN) as fh:
+        return json.load(fh)
+
+
+@pytest.fixture(scope="session")
+def golden_null_models(golden):
+    """The reference's own null models (models/null.py run in the build container), in the mirror's layout."""
+    from flemingo_b200 import objects
+    models = {t: {int(L): {"frequencies": np.array(v["frequencies"], dtype=np.float64), "bins": np.array(v["bins"], dtype=np.float64)}
+                  for L, v in d.items()} for t, d in golden["null_models"].items()}
+    objects.set_null_models(models)
+    return models
+
+
+@pytest.fixture(scope="session")
+def golden_cases(golden, golden_null_models):
+    """(case, mirror organism) pairs: organisms rebuilt from the constructor parameters with OUR host objects."""
+    from tests.helpers import build_case_organism
+    return [(case, build_case_organism(case)) for case in golden["cases"]]
+
+
+@pytest.fixture(scope="session")
+def engine():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from flemingo_b200.engine import get_engine
+    return get_engine()
