@@ -1,0 +1,208 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against (a) the committed golden fixtures that
+the reference itself produced and (b) the CPU oracle on seeded synthetic inputs.
+
+Bar: energies, node scores and placement offsets BIT-EXACT (==).  The kernels do all arithmetic in IEEE
+double in the reference's operand order, so no tolerance is needed; fitness statistics are compared at
+rtol 1e-9 (summation order of the device reduction differs from numpy's pairwise sum; north_star allows 1e-5).
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests.helpers import assert_placement_equals_golden
+
+pytestmark = pytest.mark.gpu
+
+FIT_RTOL = 1e-9
+
+
+def test_golden_cases_batched_trace(engine, golden_cases):
+    """Every golden organism on its own sequences through fl_place_batch with traceback."""
+    n = 0
+    for case, org in golden_cases:
+        engine.upload_population([org])
+        sset = engine.upload_sequences(case["sequences"], 0)
+        res = engine.place(sset, trace=True)
+        for s, ref in enumerate(case["placements"]):
+            assert_placement_equals_golden(ref, res.energies[0, s], res.rec_scores[0, s], res.con_scores[0, s], res.gaps[0, s],
+                                           org.recognizer_lengths, f"{case['name']}[{s}]")
+            n += 1
+        # the energy-only kernel variant must agree with the trace variant
+        assert np.array_equal(engine.place(sset, trace=False).energies, res.energies), case["name"]
+    assert n > 400
+
+
+def test_golden_cases_through_get_placement(engine, golden_cases):
+    """The reference-facing call: OrganismObject.get_placement -> multiplacement.calculate -> fl_calculate."""
+    for case, org in golden_cases[::3]:
+        for seq, ref in list(zip(case["sequences"], case["placements"]))[:3]:
+            p = org.get_placement(seq)
+            assert p.energy == ref["energy"], case["name"]
+            assert p.recognizers_scores == ref["recognizers_scores"]
+            assert p.connectors_scores == ref["connectors_scores"]
+            assert p.recognizers_positions == ref["recognizers_positions"]
+            assert p.connectors_positions == ref["connectors_positions"]
+            assert p.recognizer_types == org.recognizer_types
+
+
+def test_golden_population_in_one_batch(engine, golden_cases):
+    """All golden organisms that share a table length as ONE population on one ragged sequence set."""
+    by_M = {}
+    for case, org in golden_cases:
+        by_M.setdefault(case["max_seq_length"], []).append((case, org))
+    checked = 0
+    for M, group in by_M.items():
+        if M > 300:
+            continue
+        orgs = [o for _, o in group]
+        longest = max(o.sum_recognizer_lengths for o in orgs)
+        seqs = [s for c, _ in group for s in c["sequences"] if longest <= len(s) <= M]
+        if not seqs:
+            continue
+        engine.upload_population(orgs)
+        res = engine.place(engine.upload_sequences(seqs, 0), trace=True)
+        E, G, R, Cs = oracle.place_all(orgs, seqs, "restated")
+        assert np.array_equal(res.energies, E)
+        assert np.array_equal(res.gaps, G)
+        assert np.array_equal(res.rec_scores, R)
+        assert np.array_equal(res.con_scores, Cs)
+        checked += E.size
+    assert checked > 100
+
+
+def test_golden_fitness_all_methods(engine, golden_cases):
+    n = 0
+    for case, org in golden_cases:
+        if not case["fitness"]:
+            continue
+        half = case["fitness"][0]["n_pos"]
+        pos, neg = case["sequences"][:half], case["sequences"][half:]
+        engine.upload_population([org])
+        sp, sn = engine.upload_sequences(pos, 0), engine.upload_sequences(neg, 1)
+        engine.place(sp, fetch=False)
+        engine.place(sn, fetch=False)
+        for f in case["fitness"]:
+            got = engine.fitness(sp, sn, f["method"], f["gamma"])[0]
+            want = np.array([f["fitness"], f["M_p"], f["SE_p"], f["M_n"], f["SE_n"]])
+            assert np.allclose(got, want, rtol=FIT_RTOL, atol=0, equal_nan=True), (case["name"], f, got)
+            n += 1
+    assert n > 300
+
+
+def test_object_api_matches_golden_fitness(engine, golden_cases):
+    """set_fitness / get_M_and_SE_on_DNA_set / get_binding_energies keep the reference's return values."""
+    case, org = next((c, o) for c, o in golden_cases if c["name"] == "c2_shape_0")
+    half = case["fitness"][0]["n_pos"]
+    pos, neg = case["sequences"][:half], case["sequences"][half:]
+    energies = org.get_binding_energies(case["sequences"])
+    assert energies == [p["energy"] for p in case["placements"]]
+    for f in case["fitness"]:
+        org.set_fitness(pos, neg, f["method"], f["gamma"])
+        assert np.isclose(org.fitness, f["fitness"], rtol=FIT_RTOL, equal_nan=True)
+        m, se = org.get_M_and_SE_on_DNA_set(pos, f["method"], f["gamma"])
+        assert np.isclose(m, f["M_p"], rtol=FIT_RTOL, equal_nan=True) and np.isclose(se, f["SE_p"], rtol=FIT_RTOL)
+    with pytest.raises(ValueError):
+        org.set_fitness(pos, neg, "NoSuchMethod", 0.2)
+
+
+@pytest.mark.parametrize("kind,n_org,S,n_seq", [("pssm", 24, 300, 40), ("mixed", 48, 300, 24), ("mixed", 40, 97, 33)])
+def test_synthetic_population_vs_oracle(engine, kind, n_org, S, n_seq):
+    from flemingo_b200 import synthetic
+    orgs = synthetic.pssm_organisms(n_org, S, 3) if kind == "pssm" else synthetic.mixed_organisms(n_org, S, 3)
+    seqs = synthetic.random_sequences(n_seq, S, 1)
+    engine.upload_population(orgs)
+    res = engine.place(engine.upload_sequences(seqs, 0), trace=True)
+    E, G, R, Cs = oracle.place_all(orgs, seqs, "restated")
+    assert np.array_equal(res.energies, E)
+    assert np.array_equal(res.gaps, G)
+    assert np.array_equal(res.rec_scores, R)
+    assert np.array_equal(res.con_scores, Cs)
+
+
+def test_long_promoter_vs_oracle(engine):
+    """BASELINE config-4 shape: 2 kb sequences, wide gap windows (P ~ 1965)."""
+    from flemingo_b200 import synthetic
+    orgs = synthetic.pssm_organisms(3, 2000, 5, mu_range=(0, 1500))
+    seqs = synthetic.random_sequences(5, 2000, 6)
+    engine.upload_population(orgs)
+    res = engine.place(engine.upload_sequences(seqs, 0), trace=True)
+    E, G, R, Cs = oracle.place_all(orgs, seqs, "restated")
+    assert np.array_equal(res.energies, E) and np.array_equal(res.gaps, G)
+    assert np.array_equal(res.rec_scores, R) and np.array_equal(res.con_scores, Cs)
+
+
+def test_full_size_config2_properties(engine):
+    """BASELINE config 2 at full size (256 organisms x 2000 sequences of 300 bp): size-independent properties.
+
+    (1) a random sample of pairs equals the oracle bit for bit; (2) energy-only and trace kernels agree;
+    (3) energy == sum of the reported node scores in the reference's association order; (4) positions are
+    a valid chain inside the sequence; (5) duplicating a sequence duplicates its column (no cross-talk).
+    """
+    from flemingo_b200 import synthetic
+    orgs, pos, neg = synthetic.make_workload("c2")
+    seqs = pos + neg
+    seqs[1234] = seqs[7]
+    engine.upload_population(orgs)
+    sset = engine.upload_sequences(seqs, 0)
+    res = engine.place(sset, trace=True)
+    assert np.array_equal(engine.place(sset, trace=False).energies, res.energies)
+    assert np.array_equal(res.energies[:, 1234], res.energies[:, 7])
+    rng = np.random.default_rng(0)
+    for o, s in zip(rng.integers(0, len(orgs), 300), rng.integers(0, len(seqs), 300)):
+        e, rs, cs, gaps, _ = oracle.place(orgs[o], seqs[s])
+        assert res.energies[o, s] == e and np.array_equal(res.gaps[o, s, :3], gaps)
+        assert np.array_equal(res.rec_scores[o, s, :3], rs) and np.array_equal(res.con_scores[o, s, :2], cs)
+    # chain validity and energy recomposition for every pair
+    L = 12
+    g = res.gaps.astype(np.int64)
+    end = g[:, :, 0] + g[:, :, 1] + g[:, :, 2] + 3 * L
+    assert (g >= 0).all() and (end <= 300).all()
+    r, c = res.rec_scores, res.con_scores
+    recomposed = ((r[:, :, 0] + c[:, :, 0]) + r[:, :, 1] + c[:, :, 1]) + r[:, :, 2]
+    assert np.array_equal(recomposed, res.energies)
+
+
+def test_error_behaviour(engine, golden_cases):
+    from flemingo_b200 import _cabi, synthetic
+    case, org = next((c, o) for c, o in golden_cases if c["name"] == "c2_shape_0")
+    # organism longer than the sequence: ValueError, as organism_object.py:1279
+    with pytest.raises(ValueError):
+        org.get_placement("acgt" * 5)
+    engine.upload_population([org])
+    with pytest.raises(ValueError):
+        engine.place(engine.upload_sequences(["acgt" * 5], 0))
+    # sequence longer than the precomputed gap tables: legacy branch, rejected
+    with pytest.raises(_cabi.FlemingoError) as ei:
+        engine.place(engine.upload_sequences(["acgt" * 100], 0))
+    assert ei.value.code == _cabi.FL_E_UNSUPPORTED
+    # empty set and empty population
+    empty = engine.upload_sequences([], 0)
+    assert engine.place(empty).energies.shape == (1, 0)
+    assert org.get_binding_energies([]) == []
+    # NaN null bin: the reference exits the process; we raise
+    shp = synthetic.random_shape(np.random.default_rng(1), 5, "mgw")
+    shp.null_model = np.full_like(np.asarray(shp.null_model, dtype=np.float64), np.nan)
+    bad = synthetic.assemble("nan", [shp], [])
+    engine.upload_population([bad])
+    with pytest.raises(_cabi.FlemingoError) as ei:
+        engine.place(engine.upload_sequences(["acgtacgtacgt"], 0))
+    assert ei.value.code == _cabi.FL_E_NAN_NULL
+    # the context stays usable afterwards
+    engine.upload_population([org])
+    ok = engine.place(engine.upload_sequences(case["sequences"][:2], 0))
+    assert ok.energies[0, 0] == case["placements"][0]["energy"]
+
+
+def test_single_recognizer_and_tight_fits(engine):
+    """n = 1 (no connector) and P = 1 / P = 2, where -1e10 enters the energy (connector.c:53-54)."""
+    from flemingo_b200 import synthetic
+    rng = np.random.default_rng(9)
+    one = synthetic.assemble("one", [synthetic.random_pssm(rng, 7)], [])
+    three = synthetic.pssm_organisms(1, 40, 10, n_rec=3, rec_len=5)[0]
+    for org, lens in ((one, (7, 8, 30)), (three, (15, 16, 17, 40))):
+        seqs = [s for L in lens for s in synthetic.random_sequences(3, L, L)]
+        engine.upload_population([org])
+        res = engine.place(engine.upload_sequences(seqs, 0), trace=True)
+        E, G, R, Cs = oracle.place_all([org], seqs, "restated")
+        assert np.array_equal(res.energies, E) and np.array_equal(res.gaps, G)
+        assert np.array_equal(res.rec_scores, R) and np.array_equal(res.con_scores, Cs)
