@@ -283,7 +283,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         value = placements / (ms_per_step * 1e-3)
         cells, adds = cells_per_placement(orgs, w["seq_len"])
         hbm_peak, sm_max_mhz, how = load_peaks()
-        # dominant kernel = place_exact_kernel (two launches per step, one per sequence set), per GPU
+        # dominant kernel = place_tiled_kernel (two launches per step, one per sequence set), per GPU
         k_ms = place_ms / args.steps / 2
         k_pairs = n_local * n_seq / 2
         flops = k_pairs * (3.0 * cells + adds)
@@ -297,7 +297,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 "e2e": {"value": placements / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s * 1e3},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "alu", "kernel": "place_exact_kernel", "achieved": achieved, "peak": alu_peak,
+                "roofline": {"bound": "alu", "kernel": "place_tiled_kernel", "achieved": achieved, "peak": alu_peak,
                              "unit": "TFLOP/s (non-tensor flop-equivalents: 3 per DP cell + 1 per score add)",
                              "frac": achieved / alu_peak, "traffic": None,
                              "peak_source": f"{SM_COUNT} SMs x {LANES_PER_SM} lanes x {sm_max_mhz:.0f} MHz ({how} max SM clock)",

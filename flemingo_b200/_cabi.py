@@ -19,7 +19,7 @@ FIT_METHODS = {"Welch": 0, "Yuen": 1, "Trim-left-M": 2, "Trim-left-M-SD": 3}
 # every symbol include/flemingo_b200.h declares (tests check that the .so exports exactly these)
 EXPORTED = [
     "fl_last_error", "fl_abi_version", "fl_ctx_create", "fl_ctx_destroy", "fl_ctx_stream", "fl_sync",
-    "fl_upload_sequences", "fl_sequence_classes", "fl_upload_population", "fl_place_batch", "fl_fitness",
+    "fl_upload_sequences", "fl_sequence_classes", "fl_upload_population", "fl_update_connectors", "fl_place_batch", "fl_fitness",
     "fl_calculate", "fl_launch_count",
 ]
 
@@ -65,6 +65,7 @@ def load_library() -> C.CDLL:
     lib.fl_upload_sequences.argtypes = [vp, ip, vp, vp, ip]
     lib.fl_sequence_classes.argtypes = [vp, ip, C.POINTER(ip), vp]
     lib.fl_upload_population.argtypes = [vp, C.POINTER(FlPopulation)]
+    lib.fl_update_connectors.argtypes = [vp, vp, ll]
     lib.fl_place_batch.argtypes = [vp, ip, vp, ip, vp, vp, vp, vp]
     lib.fl_fitness.argtypes = [vp, ip, ip, ip, dp, vp]
     lib.fl_calculate.argtypes = [vp, vp, ip, vp, ip, vp, vp, vp, ll, vp, vp, vp, ip, vp, vp, vp]

@@ -48,420 +48,26 @@ static int fail(int code, const char *fmt, ...) {
     if (e_ != cudaSuccess) return fail(FL_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
   } while (0)
 
-// ------------------------------------------------------------------------------------------------
-// device-side constants and small structs
-// ------------------------------------------------------------------------------------------------
-#define T_MGW 0
-#define T_PROT 1024
-#define T_ROLL 2048
-#define T_HELT 4096
-#define T_DEN 6144
-
-#define BIG_NEG (-1e10)
-#define BIG_POS (1e10)
-
-constexpr int kRowTiles = 4;              // rows per lane in the simple DP kernel (32*kRowTiles rows per pass)
-constexpr int kPadLo = 32 * kRowTiles;    // -inf padding below G[0]: j-k reaches -(32*kRowTiles-1) on diagonal tiles
-constexpr int kPadHi = 32 * kRowTiles;    // padding above G[P-1]: rows of the last pass may exceed P-1
-constexpr int kMaxSmem = 232448;          // 227 KB opt-in limit per CTA on sm_100
-
-#define ERR_NAN_NULL 1
-
-struct RecDesc {
-  int kind;  // 0 PSSM, 1 MGW, 2 ProT, 3 Roll, 4 HelT
-  int len;
-  int nb;    // number of bin edges (shape only)
-  int data;  // offset into the organism's slice of the recognizer pool (doubles)
-  int fwd;   // sum of the lengths of the recognizers before this one (organism.c:273,392)
-  int pad;
-};
-
-struct PlaceParams {
-  // population (device pointers)
-  const int *rec_begin;
-  const char *rec_type;
-  const int *rec_len;
-  const int *rec_nb;
-  const long long *rec_data;
-  const long long *pool_begin;
-  const double *rec_pool;
-  const int *con_M;
-  const double *con_pool;
-  const long long *con_begin;  // [n_org] for this class
-  const int *sum_len;
-  // sequence set
-  const unsigned *packed;
-  const unsigned *unk;
-  const int *word_off;
-  const int *unk_off;
-  const int *order;
-  int class_begin, class_count, S, n_seq_total;
-  // data tables
-  const double *tables;
-  // outputs
-  double *E;
-  int *gaps;
-  double *rsc;
-  double *csc;
-  int max_rec;
-  int *err_flag;
-  // plan
-  int seqs_per_cta, chunks;
-  int pool_stride, g_stride, row_stride, code_stride, nrows;
-};
-
-__device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xfff0000000000000LL); }
-
-// Score of one recognizer at one offset.  `codes` already points at the recognizer's first admissible base
-// (sequence + forward offset, organism.c:328).  Codes: 0..3 = A,G,C,T; 4 = any other byte.
-__device__ __forceinline__ double score_rec(const RecDesc &r, const double *s_pool, const unsigned char *codes, int pos,
-                                            const double *__restrict__ tables, int &err) {
-  const unsigned char *c = codes + pos;
-  if (r.kind == 0) {
-    // recognizer.c:130-168: left-to-right sum from 0.0; an unknown byte adds nothing
-    const double *m = s_pool + r.data;
-    double s = 0.0;
-    for (int col = 0; col < r.len; ++col) {
-      const int b = c[col];
-      if (b < 4) s += m[4 * col + b];
-    }
-    return s;
-  }
-  const int np = r.len - 4;
-  double score;
-  // pentamer index: sum code * 4^(4-k), unknown bytes count as 0 (recognizer.c:219-241 has no default case)
-  int idx = 0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) idx = idx * 4 + (c[k] & 3) * (c[k] < 4);
-  if (r.kind <= 2) {
-    // _aux.c:211-217
-    const double *tab = tables + (r.kind == 1 ? T_MGW : T_PROT);
-    double sum = 0.0;
-    for (int j = 0; j < np; ++j) {
-      idx = ((idx << 2) | ((c[j + 4] & 3) * (c[j + 4] < 4))) & 1023;
-      sum += __ldg(tab + idx);
-    }
-    score = sum / (double)np;
-  } else {
-    // _aux.c:203-209 on pent = [TAB[idx_0..]] ++ [TAB[1024+idx_0..]] (recognizer.c:447-450)
-    const double *tab = tables + (r.kind == 3 ? T_ROLL : T_HELT);
-    const int idx0 = ((idx << 2) | ((c[4] & 3) * (c[4] < 4))) & 1023;
-    int idxl = 0;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) idxl = idxl * 4 + (c[np - 1 + k] & 3) * (c[np - 1 + k] < 4);
-    double sum = __ldg(tab + idx0) + __ldg(tab + 1024 + idxl);
-    int id = idx;
-    for (int j = 0; j < np; ++j) {
-      id = ((id << 2) | ((c[j + 4] & 3) * (c[j + 4] < 4))) & 1023;
-      sum += __ldg(tab + id);
-    }
-    id = idx;
-    for (int j = 0; j < np; ++j) {
-      id = ((id << 2) | ((c[j + 4] & 3) * (c[j + 4] < 4))) & 1023;
-      sum += __ldg(tab + 1024 + id);
-    }
-    score = sum / (double)(2 * np + 2);
-  }
-  // _aux.c:184-190: first bin with edges[b-1] <= score < edges[b], otherwise the last bin
-  const double *nullf = s_pool + r.data;
-  const double *altf = nullf + (r.nb - 1);
-  const double *edges = altf + (r.nb - 1);
-  int b = 1;
-  for (; b < r.nb; ++b)
-    if (score >= edges[b - 1] && score < edges[b]) break;
-  if (b == r.nb) b = r.nb - 1;
-  const double n0 = nullf[b - 1];
-  double v = altf[b - 1] - n0;
-  if (v < BIG_NEG) v = BIG_NEG;
-  if (n0 != n0) err |= ERR_NAN_NULL;
-  return v;
-}
-
-// connector.c:35-66 for one gap length; D = DEN_EXPANSION
-__device__ __forceinline__ double gap_energy(const double *__restrict__ pdf, double auc, int g, int n, int eff,
-                                             const double *__restrict__ D) {
-  if (g + n + 1 <= eff) {
-    double num = __ldg(pdf + g);
-    if (num < BIG_NEG) num = BIG_NEG;
-    num -= auc;
-    const double den = (__ldg(D + (eff - (g + 1)) - 1) - __ldg(D + (n - 1) - 1) - __ldg(D + eff - (g + 1) - (n - 1) - 1)) -
-                       (__ldg(D + eff - 1) - __ldg(D + n - 1) - __ldg(D + eff - n - 1));
-    double res = num - den;
-    if (res < BIG_NEG) return BIG_NEG;
-    if (res > BIG_POS) return BIG_POS;
-    return res;
-  }
-  return BIG_NEG;
-}
-
-// ------------------------------------------------------------------------------------------------
-// K1+K2 fused, exact fp64: one CTA = one organism x a chunk of sequences of one length class;
-// one warp = one (organism, sequence) pair at a time.
-// ------------------------------------------------------------------------------------------------
-template <bool TRACE>
-__global__ void __launch_bounds__(256) place_exact_kernel(const PlaceParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int o = blockIdx.x / p.chunks;
-  const int chunk = blockIdx.x - o * p.chunks;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const int rb = p.rec_begin[o];
-  const int n = p.rec_begin[o + 1] - rb;
-  const int S = p.S;
-  const int sumL = p.sum_len[o];
-  const int P = S - sumL + 1;
-  const int eff = S - sumL + n;
-
-  double *s_pool = reinterpret_cast<double *>(smem_raw);
-  double *s_G = s_pool + p.pool_stride;
-  double *s_rows = s_G + (size_t)(p.max_rec - 1) * p.g_stride;
-  RecDesc *s_rec = reinterpret_cast<RecDesc *>(s_rows + (size_t)nwarps * p.nrows * p.row_stride);
-  unsigned char *s_codes = reinterpret_cast<unsigned char *>(s_rec + p.max_rec);
-
-  // ---- organism prologue: tables into shared memory, gap-energy tables G[c][g] -------------------
-  {
-    const long long pb = p.pool_begin[o];
-    const int pn = (int)(p.pool_begin[o + 1] - pb);
-    for (int i = tid; i < pn; i += blockDim.x) s_pool[i] = __ldg(p.rec_pool + pb + i);
-    if (tid == 0) {
-      int fwd = 0;
-      for (int i = 0; i < n; ++i) {
-        RecDesc d;
-        const char t = p.rec_type[rb + i];
-        d.kind = (t == 'p' || t == 'P') ? 0 : (t == 'm' || t == 'M') ? 1 : (t == 't' || t == 'T') ? 2 : (t == 'r' || t == 'R') ? 3 : 4;
-        d.len = p.rec_len[rb + i];
-        d.nb = p.rec_nb[rb + i];
-        d.data = (int)(p.rec_data[rb + i] - pb);
-        d.fwd = fwd;
-        d.pad = 0;
-        fwd += d.len;
-        s_rec[i] = d;
-      }
-    }
-    const int M = p.con_M[o];
-    const double *D = p.tables + T_DEN;
-    for (int c = 0; c < n - 1; ++c) {
-      const double *pdf = p.con_pool + p.con_begin[o] + (long long)c * (2 * M + 2) + 2;
-      const double auc = __ldg(pdf + (M - 1) + (S - sumL));  // cdf pointer = pdf + max_len, max_len = M-1 (connector.c:3-4)
-      double *Gc = s_G + (size_t)c * p.g_stride;
-      for (int i = tid; i < p.g_stride; i += blockDim.x) {
-        const int g = i - kPadLo;
-        Gc[i] = (g < 0 || g >= P) ? neg_inf() : gap_energy(pdf, auc, g, n, eff, D);
-      }
-    }
-  }
-  __syncthreads();
-
-  double *rows = s_rows + (size_t)warp * p.nrows * p.row_stride;
-  unsigned char *codes = s_codes + (size_t)warp * p.code_stride;
-  int err = 0;
-
-  const int first = chunk * p.seqs_per_cta;
-  const int last = min(p.class_count, first + p.seqs_per_cta);
-  for (int si = first + warp; si < last; si += nwarps) {
-    const int seq = p.order[p.class_begin + si];
-    // ---- unpack 2-bit bases (+ unknown mask) into byte codes ------------------------------------
-    {
-      const unsigned *pw = p.packed + p.word_off[seq];
-      const unsigned *uw = p.unk + p.unk_off[seq];
-      for (int b = lane; b < S; b += 32) {
-        const unsigned w = __ldg(pw + (b >> 4));
-        const unsigned u = __ldg(uw + (b >> 5));
-        const unsigned code = (w >> (2 * (b & 15))) & 3u;
-        codes[b] = ((u >> (b & 31)) & 1u) ? 4 : (unsigned char)code;
-      }
-    }
-    __syncwarp();
-
-    // ---- stage 0: C_0 = R_0 (organism.c:381-385) ------------------------------------------------
-    for (int j = lane; j < P; j += 32) rows[j] = score_rec(s_rec[0], s_pool, codes, j, p.tables, err);
-    __syncwarp();
-
-    // ---- stages 1..n-1: C_i[j] = max_k (C_{i-1}[k] + G[j-k]) + R_i[j] (organism.c:347-369) --------
-    for (int i = 1; i < n; ++i) {
-      const double *prev = rows + (size_t)(TRACE ? (i - 1) : ((i - 1) & 1)) * p.row_stride;
-      double *cur = rows + (size_t)(TRACE ? i : (i & 1)) * p.row_stride;
-      const double *Gc = s_G + (size_t)(i - 1) * p.g_stride + kPadLo;
-      const RecDesc rd = s_rec[i];
-      const unsigned char *ci = codes + rd.fwd;
-      for (int jb = 0; jb < P; jb += 32 * kRowTiles) {
-        double acc[kRowTiles];
-#pragma unroll
-        for (int t = 0; t < kRowTiles; ++t) acc[t] = neg_inf();
-        const double *gp = Gc + jb + lane;
-        const int kend = min(P, jb + 32 * kRowTiles);
-#pragma unroll 2
-        for (int k = 0; k < kend; ++k) {
-          const double pv = prev[k];
-#pragma unroll
-          for (int t = 0; t < kRowTiles; ++t) {
-            const double cand = pv + gp[32 * t - k];
-            acc[t] = (acc[t] < cand) ? cand : acc[t];
-          }
-        }
-#pragma unroll
-        for (int t = 0; t < kRowTiles; ++t) {
-          const int j = jb + lane + 32 * t;
-          if (j < P) cur[j] = acc[t] + score_rec(rd, s_pool, ci, j, p.tables, err);
-        }
-      }
-      __syncwarp();
-    }
-
-    // ---- first maximum of the last row (_aux.c:149-158) ------------------------------------------
-    const double *lastrow = rows + (size_t)(TRACE ? (n - 1) : ((n - 1) & 1)) * p.row_stride;
-    double bv = neg_inf();
-    int bi = 0x7fffffff;
-    for (int j = lane; j < P; j += 32) {
-      const double v = lastrow[j];
-      if (bi == 0x7fffffff || v > bv) { bv = v; bi = j; }
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-      if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
-    }
-    const size_t pair = (size_t)o * p.n_seq_total + seq;
-    if (lane == 0) p.E[pair] = bv;
-
-    // ---- traceback (organism.c:398-427): re-scan one column per stage for the first k that reproduces
-    //      the stored value exactly -- identical to the reference's strict '<' update rule -------------
-    if (TRACE) {
-      int m = bi;
-      for (int i = n - 1; i >= 1; --i) {
-        const double *prev = rows + (size_t)(i - 1) * p.row_stride;
-        const double *Gc = s_G + (size_t)(i - 1) * p.g_stride + kPadLo;
-        const RecDesc rd = s_rec[i];
-        const double ri = score_rec(rd, s_pool, codes + rd.fwd, m, p.tables, err);
-        const double target = rows[(size_t)i * p.row_stride + m];
-        int found = -1;
-        for (int kb = 0; kb <= m && found < 0; kb += 32) {
-          const int k = kb + lane;
-          const bool hit = (k <= m) && ((prev[k] + Gc[m - k]) + ri == target);
-          const unsigned bal = __ballot_sync(0xffffffffu, hit);
-          if (bal) found = kb + __ffs(bal) - 1;
-        }
-        const int gap = found < 0 ? 0 : m - found;  // nothing ever won: the reference keeps its calloc'ed zeros
-        if (lane == 0) {
-          p.rsc[pair * p.max_rec + i] = ri;
-          p.csc[pair * p.max_rec + i - 1] = found < 0 ? 0.0 : Gc[gap];
-          p.gaps[pair * p.max_rec + i] = gap;
-        }
-        m -= gap;
-      }
-      if (lane == 0) {
-        p.rsc[pair * p.max_rec] = rows[m];
-        p.gaps[pair * p.max_rec] = m;
-      }
-    }
-    __syncwarp();
-  }
-  if (err) atomicOr(p.err_flag, err);
-}
-
-// ------------------------------------------------------------------------------------------------
-// K3: per-organism fitness statistic (organism_object.py:848-956).  One CTA per organism.
-// ------------------------------------------------------------------------------------------------
-__device__ double block_sum(double v, double *s_red) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-  __syncthreads();
-  if (lane == 0) s_red[warp] = v;
-  __syncthreads();
-  double t = 0.0;
-  for (int w = 0; w < nw; ++w) t += s_red[w];
-  return t;
-}
-
-// in-place bitonic sort of n2 (power of two) doubles by one CTA
-__device__ void block_bitonic_sort(double *a, int n2) {
-  for (int k = 2; k <= n2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < n2; i += blockDim.x) {
-        const int l = i ^ j;
-        if (l > i) {
-          const double x = a[i], y = a[l];
-          const bool up = ((i & k) == 0);
-          if ((x > y) == up) { a[i] = y; a[l] = x; }
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
-
-struct SetStat {
-  double mean, se;
-};
-
-// mean / standard error of one organism's energies on one set; `scratch` (n2 doubles) is used by the
-// trimmed variants.  lo/hi = number of elements dropped from the sorted ends for the mean.
-__device__ SetStat set_stat(const double *__restrict__ e, int n, int method, int n_trim, double *scratch, int n2,
-                            double *s_red) {
-  SetStat r;
-  const double *src = e;
-  int lo = 0, hi = n;          // mean over sorted[lo:hi]
-  int sd_lo = 0, sd_hi = n;    // std over [sd_lo:sd_hi]
-  bool empty_mean = false;
-  if (n_trim != 0 && method != FL_FIT_WELCH) {
-    for (int i = threadIdx.x; i < n2; i += blockDim.x) scratch[i] = i < n ? e[i] : __longlong_as_double(0x7ff0000000000000LL);
-    __syncthreads();
-    block_bitonic_sort(scratch, n2);
-    src = scratch;
-    if (method == FL_FIT_YUEN) {
-      const int t = min(n_trim, (n - 1) / 2);
-      lo = t;
-      hi = n - t;
-      if (t == 0) empty_mean = true;  // python: energy_scores[0:-0] is the empty list
-    } else {
-      lo = min(n_trim, n);
-      if (method == FL_FIT_TRIM_LEFT_M_SD) sd_lo = lo;
-    }
-  }
-  const int cnt = hi - lo;
-  double acc = 0.0;
-  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) acc += src[i];
-  const double total = block_sum(acc, s_red);
-  r.mean = (cnt <= 0 || empty_mean) ? __longlong_as_double(0x7ff8000000000000LL) : total / (double)cnt;
-  // np.std(ddof=1): mean of the std window, then sum of squared deviations / (N-1)
-  const int scnt = sd_hi - sd_lo;
-  double a2 = 0.0;
-  for (int i = sd_lo + threadIdx.x; i < sd_hi; i += blockDim.x) a2 += src[i];
-  const double smean = block_sum(a2, s_red) / (double)scnt;
-  double q = 0.0;
-  for (int i = sd_lo + threadIdx.x; i < sd_hi; i += blockDim.x) {
-    const double d = src[i] - smean;
-    q += d * d;
-  }
-  const double ss = block_sum(q, s_red);
-  double sd = sqrt(ss / (double)(scnt - 1));
-  if (!(sd > 1.0)) sd = 1.0;  // max(1, stdev): python's max keeps 1 when stdev is nan (N == 1)
-  r.se = sd / sqrt((double)scnt);
-  return r;
-}
-
-__global__ void __launch_bounds__(256) fitness_kernel(const double *__restrict__ Epos, int n_pos, const double *__restrict__ Eneg,
-                                                      int n_neg, int method, int trim_pos, int trim_neg, double *scratch,
-                                                      int n2, double *__restrict__ out) {
-  __shared__ double s_red[32];
-  const int o = blockIdx.x;
-  double *sc = scratch + (size_t)o * n2;
-  const SetStat sp = set_stat(Epos + (size_t)o * n_pos, n_pos, method, trim_pos, sc, n2, s_red);
-  __syncthreads();
-  const SetStat sn = set_stat(Eneg + (size_t)o * n_neg, n_neg, method, trim_neg, sc, n2, s_red);
-  if (threadIdx.x == 0) {
-    out[o * 5 + 0] = (sp.mean - sn.mean) / sqrt(sp.se * sp.se + sn.se * sn.se);
-    out[o * 5 + 1] = sp.mean;
-    out[o * 5 + 2] = sp.se;
-    out[o * 5 + 3] = sn.mean;
-    out[o * 5 + 4] = sn.se;
-  }
-}
+#include "place_kernel.cuh"
+#include "fitness_kernel.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // host side: context, uploads, launch planning
 // ------------------------------------------------------------------------------------------------
+typedef void (*place_kernel_fn)(const PlaceParams);
+constexpr int kNumTileSizes = 5;
+static const int kTileSizes[kNumTileSizes] = {1, 3, 5, 7, 9};  // odd: lane stride J doubles is bank-conflict free
+static const place_kernel_fn kPlaceKernels[kNumTileSizes][2] = {
+    {place_tiled_kernel<1, false>, place_tiled_kernel<1, true>}, {place_tiled_kernel<3, false>, place_tiled_kernel<3, true>},
+    {place_tiled_kernel<5, false>, place_tiled_kernel<5, true>}, {place_tiled_kernel<7, false>, place_tiled_kernel<7, true>},
+    {place_tiled_kernel<9, false>, place_tiled_kernel<9, true>}};
+
+// Tile size for P offsets: the smallest J whose single folded round (64 blocks) covers P, so that most lanes are busy.
+static int pick_tile(int P) {
+  for (int j = 0; j < kNumTileSizes; ++j)
+    if (64 * kTileSizes[j] >= P) return j;
+  return kNumTileSizes - 1;
+}
 struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
@@ -510,7 +116,7 @@ struct Population {
 struct fl_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  DevBuf tables, err_flag, con_begin, gaps, rsc, csc, fit_out, fit_scratch;
+  DevBuf tables, err_flag, con_begin, org_list, gaps, rsc, csc, fit_out, fit_scratch;
   Population pop, scratch_pop;
   SeqSet sets[FL_MAX_SETS + 1];  // the extra slot serves fl_calculate
   long long launches = 0;
@@ -542,8 +148,10 @@ extern "C" int fl_ctx_create(int device, const double *tables, long long n_table
   CK(cudaMemcpyAsync(ctx->tables.p, tables, sizeof(double) * FL_N_TABLE_DOUBLES, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(ctx->err_flag.p, 0, sizeof(int), ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  CK(cudaFuncSetAttribute(place_exact_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-  CK(cudaFuncSetAttribute(place_exact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+  for (int j = 0; j < kNumTileSizes; ++j) {
+    CK(cudaFuncSetAttribute(kPlaceKernels[j][0], cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CK(cudaFuncSetAttribute(kPlaceKernels[j][1], cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+  }
   *out = ctx;
   return FL_OK;
 }
@@ -563,7 +171,7 @@ extern "C" int fl_ctx_destroy(fl_ctx *ctx) {
   }
   release_pop(ctx->pop);
   release_pop(ctx->scratch_pop);
-  DevBuf *bufs[] = {&ctx->tables, &ctx->err_flag, &ctx->con_begin, &ctx->gaps, &ctx->rsc, &ctx->csc, &ctx->fit_out, &ctx->fit_scratch};
+  DevBuf *bufs[] = {&ctx->tables, &ctx->err_flag, &ctx->con_begin, &ctx->org_list, &ctx->gaps, &ctx->rsc, &ctx->csc, &ctx->fit_out, &ctx->fit_scratch};
   for (DevBuf *b : bufs) b->release();
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -739,6 +347,20 @@ extern "C" int fl_upload_population(fl_ctx *ctx, const fl_population *pop) {
   return upload_population(ctx, ctx->pop, pop);
 }
 
+extern "C" int fl_update_connectors(fl_ctx *ctx, const double *con_pool, long long n_con) {
+  if (!ctx || (n_con > 0 && !con_pool)) return fail(FL_E_ARG, "fl_update_connectors: null argument");
+  if (!ctx->pop.valid) return fail(FL_E_STATE, "fl_update_connectors: no population uploaded");
+  if (n_con < ctx->pop.n_con) return fail(FL_E_ARG, "fl_update_connectors: the pool may only grow (%lld -> %lld doubles)", ctx->pop.n_con, n_con);
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));  // kernels in flight still read the old pool
+  int rc = ctx->pop.d_con_pool.ensure((size_t)n_con * 8 + 8);
+  if (rc) return rc;
+  if (n_con) CK(cudaMemcpyAsync(ctx->pop.d_con_pool.p, con_pool, (size_t)n_con * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->pop.n_con = n_con;
+  return FL_OK;
+}
+
 static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long *con_begin, int flags, double *energies,
                        int *gaps, double *rec_scores, double *con_scores) {
   if (!P.valid) return fail(FL_E_STATE, "fl_place_batch: no population uploaded");
@@ -774,6 +396,7 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
   int rc;
   if ((rc = set.E.ensure((size_t)n_org * n_seq * 8))) return rc;
   if ((rc = ctx->con_begin.ensure((size_t)n_cls * n_org * 8))) return rc;
+  if ((rc = ctx->org_list.ensure((size_t)n_cls * n_org * 4))) return rc;
   if (trace) {
     const size_t cells = (size_t)n_org * n_seq * P.max_rec;
     if ((rc = ctx->gaps.ensure(cells * 4)) || (rc = ctx->rsc.ensure(cells * 8)) || (rc = ctx->csc.ensure(cells * 8))) return rc;
@@ -819,8 +442,8 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
 
     const int Pmax = cl.len - P.min_sum_len + 1;
     pp.pool_stride = (P.max_pool + 1) & ~1;
-    pp.g_stride = kPadLo + Pmax + kPadHi;
-    pp.row_stride = (Pmax + 3) & ~3;
+    pp.g_stride = (kGPad + Pmax + kGPad + 1) & ~1;
+    pp.row_stride = (Pmax + kMaxJ + 3) & ~3;
     pp.code_stride = (cl.len + 15) & ~15;
     pp.nrows = trace ? P.max_rec : std::min(2, P.max_rec);
     int nwarps = 8;
@@ -834,22 +457,36 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
     }
     if (smem > (size_t)kMaxSmem)
       return fail(FL_E_UNSUPPORTED, "placement of %d offsets x %d recognizers needs %zu bytes of shared memory (limit %d)", Pmax, P.max_rec, smem, kMaxSmem);
-    // chunking: enough CTAs to fill the machine a few times over, at least one sequence per warp
-    const long long pairs = (long long)n_org * cl.count;
-    long long target_ctas = (long long)n_sm * 16;
-    int spc = (int)std::max<long long>(nwarps, (pairs + target_ctas - 1) / target_ctas);
-    spc = std::min(spc, std::max(nwarps, 64));
-    spc = ((spc + nwarps - 1) / nwarps) * nwarps;
-    pp.seqs_per_cta = spc;
-    pp.chunks = (cl.count + spc - 1) / spc;
-    const long long grid = (long long)n_org * pp.chunks;
-    if (grid > 0x7fffffffLL) return fail(FL_E_UNSUPPORTED, "grid too large");
-    if (trace)
-      place_exact_kernel<true><<<(unsigned)grid, nwarps * 32, smem, ctx->stream>>>(pp);
-    else
-      place_exact_kernel<false><<<(unsigned)grid, nwarps * 32, smem, ctx->stream>>>(pp);
-    CK(cudaGetLastError());
-    ctx->launches++;
+    // organisms are bucketed by tile size (a compile-time constant of the kernel); one launch per bucket
+    std::vector<int> bucket[kNumTileSizes];
+    for (int o = 0; o < n_org; ++o) bucket[pick_tile(cl.len - P.sum_len[o] + 1)].push_back(o);
+    std::vector<int> list;
+    list.reserve(n_org);
+    int begin_of[kNumTileSizes];
+    for (int j = 0; j < kNumTileSizes; ++j) {
+      begin_of[j] = (int)list.size();
+      list.insert(list.end(), bucket[j].begin(), bucket[j].end());
+    }
+    int *d_list = ctx->org_list.as<int>() + (size_t)c * n_org;
+    CK(cudaMemcpyAsync(d_list, list.data(), (size_t)n_org * 4, cudaMemcpyHostToDevice, ctx->stream));
+    for (int j = 0; j < kNumTileSizes; ++j) {
+      const int n_b = (int)bucket[j].size();
+      if (!n_b) continue;
+      pp.org_list = d_list + begin_of[j];
+      // chunking: enough CTAs to fill the machine a few times over, at least one sequence per warp
+      const long long pairs = (long long)n_b * cl.count;
+      const long long target_ctas = (long long)n_sm * 16;
+      int spc = (int)std::max<long long>(nwarps, (pairs + target_ctas - 1) / target_ctas);
+      spc = std::min(spc, std::max(nwarps, 64));
+      spc = ((spc + nwarps - 1) / nwarps) * nwarps;
+      pp.seqs_per_cta = spc;
+      pp.chunks = (cl.count + spc - 1) / spc;
+      const long long grid = (long long)n_b * pp.chunks;
+      if (grid > 0x7fffffffLL) return fail(FL_E_UNSUPPORTED, "grid too large");
+      kPlaceKernels[j][trace ? 1 : 0]<<<(unsigned)grid, nwarps * 32, smem, ctx->stream>>>(pp);
+      CK(cudaGetLastError());
+      ctx->launches++;
+    }
   }
   set.E_n_org = n_org;
   set.E_valid = true;

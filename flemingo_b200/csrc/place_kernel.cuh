@@ -1,0 +1,423 @@
+// place_kernel.cuh -- K1 + K2 fused: recognizer score rows, gap-energy tables, chain-placement DP, argmax and
+// traceback, exact in IEEE double (included by flemingo_b200.cu).
+//
+// Reference semantics (paths relative to /root/reference/extensions/multiplacement/src):
+//   score rows   organism/recognizer.c:130-168 (PSSM), :187-589 (shape), _aux.c:184-217
+//   gap energy   organism/connector.c:31-66, auc pick organism/organism.c:336-340
+//   DP           organism/organism.c:321-393       argmax + traceback  _aux.c:149-158, organism.c:398-427
+//
+// Work decomposition
+//   CTA  = one organism x a chunk of sequences of one length class: PSSM / shape tables and the gap-energy tables
+//          G[c][g] (sequence independent; the reference recomputes them per DP cell) live in shared memory.
+//   warp = one (organism, sequence) pair at a time; its cumulative rows C_i[0..P) live in shared memory.
+//   lane = blocks of J consecutive offsets j.  For a block the lane walks k upward in steps of J keeping
+//          J accumulators and a 2J-wide sliding window of G in REGISTERS, so a J x J tile of DP cells costs
+//          2J shared-memory loads (J of prev, J of G) instead of J*J.
+//   The k <= j triangle is balanced by FOLDING: a lane owns block b and block NB-1-b of a round of <= 64 blocks,
+//   so every lane executes the same number of tiles; both jobs run through ONE loop so the warp never diverges
+//   in the hot code.
+#pragma once
+
+#define T_MGW 0
+#define T_PROT 1024
+#define T_ROLL 2048
+#define T_HELT 4096
+#define T_DEN 6144
+
+#define BIG_NEG (-1e10)
+#define BIG_POS (1e10)
+
+constexpr int kGPad = 16;          // -inf entries on both sides of every G table (>= largest tile size J)
+constexpr int kMaxSmem = 232448;   // 227 KB opt-in limit per CTA on sm_100
+constexpr int kMaxJ = 9;
+
+#define ERR_NAN_NULL 1
+
+struct RecDesc {
+  int kind;  // 0 PSSM, 1 MGW, 2 ProT, 3 Roll, 4 HelT
+  int len;
+  int nb;    // number of bin edges (shape only)
+  int data;  // offset into the organism's slice of the recognizer pool (doubles)
+  int fwd;   // sum of the lengths of the recognizers before this one (organism.c:273,392)
+  int pad;
+};
+
+struct PlaceParams {
+  // population (device pointers)
+  const int *rec_begin;
+  const char *rec_type;
+  const int *rec_len;
+  const int *rec_nb;
+  const long long *rec_data;
+  const long long *pool_begin;
+  const double *rec_pool;
+  const int *con_M;
+  const double *con_pool;
+  const long long *con_begin;  // [n_org] for this class
+  const int *sum_len;
+  const int *org_list;         // organisms handled by this launch (all share the tile size J)
+  // sequence set
+  const unsigned *packed;
+  const unsigned *unk;
+  const int *word_off;
+  const int *unk_off;
+  const int *order;
+  int class_begin, class_count, S, n_seq_total;
+  // data tables
+  const double *tables;
+  // outputs
+  double *E;
+  int *gaps;
+  double *rsc;
+  double *csc;
+  int max_rec;
+  int *err_flag;
+  // plan
+  int seqs_per_cta, chunks;
+  int pool_stride, g_stride, row_stride, code_stride, nrows;
+};
+
+__device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xfff0000000000000LL); }
+
+__device__ __forceinline__ int code0(unsigned char c) { return (c & 3) * (c < 4); }
+
+// Score of one recognizer at one offset.  `codes` already points at the recognizer's first admissible base
+// (sequence + forward offset, organism.c:328).  Codes: 0..3 = A,G,C,T; 4 = any other byte.
+__device__ __noinline__ double score_shape(const RecDesc &r, const double *s_pool, const unsigned char *c,
+                                           const double *__restrict__ tables, int &err) {
+  const int np = r.len - 4;
+  double score;
+  // pentamer index: sum code * 4^(4-k), unknown bytes count as 0 (recognizer.c:219-241 has no default case)
+  int idx = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) idx = idx * 4 + code0(c[k]);
+  if (r.kind <= 2) {
+    // _aux.c:211-217
+    const double *tab = tables + (r.kind == 1 ? T_MGW : T_PROT);
+    double sum = 0.0;
+    for (int j = 0; j < np; ++j) {
+      idx = ((idx << 2) | code0(c[j + 4])) & 1023;
+      sum += __ldg(tab + idx);
+    }
+    score = sum / (double)np;
+  } else {
+    // _aux.c:203-209 on pent = [TAB[idx_0..]] ++ [TAB[1024+idx_0..]] (recognizer.c:447-450)
+    const double *tab = tables + (r.kind == 3 ? T_ROLL : T_HELT);
+    const int idx0 = ((idx << 2) | code0(c[4])) & 1023;
+    int idxl = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) idxl = idxl * 4 + code0(c[np - 1 + k]);
+    double sum = __ldg(tab + idx0) + __ldg(tab + 1024 + idxl);
+    int id = idx;
+    for (int j = 0; j < np; ++j) {
+      id = ((id << 2) | code0(c[j + 4])) & 1023;
+      sum += __ldg(tab + id);
+    }
+    id = idx;
+    for (int j = 0; j < np; ++j) {
+      id = ((id << 2) | code0(c[j + 4])) & 1023;
+      sum += __ldg(tab + 1024 + id);
+    }
+    score = sum / (double)(2 * np + 2);
+  }
+  // _aux.c:184-190: first bin with edges[b-1] <= score < edges[b], otherwise the last bin
+  const double *nullf = s_pool + r.data;
+  const double *altf = nullf + (r.nb - 1);
+  const double *edges = altf + (r.nb - 1);
+  int b = 1;
+  for (; b < r.nb; ++b)
+    if (score >= edges[b - 1] && score < edges[b]) break;
+  if (b == r.nb) b = r.nb - 1;
+  const double n0 = nullf[b - 1];
+  double v = altf[b - 1] - n0;
+  if (v < BIG_NEG) v = BIG_NEG;
+  if (n0 != n0) err |= ERR_NAN_NULL;
+  return v;
+}
+
+__device__ __forceinline__ double score_rec(const RecDesc &r, const double *s_pool, const unsigned char *codes, int pos,
+                                            const double *__restrict__ tables, int &err) {
+  const unsigned char *c = codes + pos;
+  if (r.kind == 0) {
+    // recognizer.c:130-168: left-to-right sum from 0.0; an unknown byte adds nothing
+    const double *m = s_pool + r.data;
+    double s = 0.0;
+    for (int col = 0; col < r.len; ++col) {
+      const int b = c[col];
+      if (b < 4) s += m[4 * col + b];
+    }
+    return s;
+  }
+  return score_shape(r, s_pool, c, tables, err);
+}
+
+// connector.c:35-66 for one gap length; D = DEN_EXPANSION
+__device__ __forceinline__ double gap_energy(const double *__restrict__ pdf, double auc, int g, int n, int eff,
+                                             const double *__restrict__ D) {
+  if (g + n + 1 <= eff) {
+    double num = __ldg(pdf + g);
+    if (num < BIG_NEG) num = BIG_NEG;
+    num -= auc;
+    const double den = (__ldg(D + (eff - (g + 1)) - 1) - __ldg(D + (n - 1) - 1) - __ldg(D + eff - (g + 1) - (n - 1) - 1)) -
+                       (__ldg(D + eff - 1) - __ldg(D + n - 1) - __ldg(D + eff - n - 1));
+    double res = num - den;
+    if (res < BIG_NEG) return BIG_NEG;
+    if (res > BIG_POS) return BIG_POS;
+    return res;
+  }
+  return BIG_NEG;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One DP stage for one pair, executed by one warp:  cur[j] = max_{k<=j} (prev[k] + G[j-k]),  j < P.
+// (R_i[j] is added afterwards by the caller; fl(max + r) == max fl(. + r) because x -> fl(x+r) is monotone.)
+// G points at gap 0 and is readable on [-kGPad, P-1+kGPad] with -inf outside [0, P).
+// prev must be readable up to ceil(P/J)*J - 1 (values beyond P-1 are never selected: their G is -inf).
+// ------------------------------------------------------------------------------------------------
+template <int J>
+struct TileState {
+  int b;      // row block of the current job (rows b*J .. b*J+J-1)
+  int kb;     // next k block
+  int kend;   // number of k blocks of the current job (b+1); -1 when idle
+  int kstep;  // 1 while working, 0 when idle
+  int next_b; // row block of the second job, or -1
+};
+
+template <int J>
+__device__ __forceinline__ void tile_step(double (&A)[J], double (&B)[J], double (&acc)[J], TileState<J> &st,
+                                          const double *__restrict__ prev, double *__restrict__ cur,
+                                          const double *__restrict__ G, int P) {
+  if (st.kb == st.kend) {
+    // job finished: flush its rows, then start the folded partner block (or idle)
+    const int r0 = st.b * J;
+#pragma unroll
+    for (int t = 0; t < J; ++t)
+      if (r0 + t < P) cur[r0 + t] = acc[t];
+    if (st.next_b >= 0) {
+      st.b = st.next_b;
+      st.next_b = -1;
+      st.kend = st.b + 1;
+    } else {
+      st.b = 0;
+      st.kend = -1;
+      st.kstep = 0;
+    }
+    st.kb = 0;
+    const double *ga = G + st.b * J + (J - 1);
+#pragma unroll
+    for (int t = 0; t < J; ++t) {
+      acc[t] = neg_inf();
+      A[t] = ga[-t];
+    }
+  }
+  // A[i] = G[c - i], B[i] = G[c - J - i] with c = (b - kb)*J + J-1: row t at step u needs G[(b-kb)*J + t - u]
+  const double *gb = G + (st.b - st.kb) * J - 1;
+  const double *pk = prev + st.kb * J;
+  double pv[J];
+#pragma unroll
+  for (int u = 0; u < J; ++u) {
+    B[u] = gb[-u];
+    pv[u] = pk[u];
+  }
+#pragma unroll
+  for (int u = 0; u < J; ++u) {
+#pragma unroll
+    for (int t = 0; t < J; ++t) {
+      const double g = (u <= t) ? A[J - 1 - t + u] : B[u - t - 1];
+      const double cand = pv[u] + g;
+      acc[t] = (acc[t] < cand) ? cand : acc[t];
+    }
+  }
+  st.kb += st.kstep;
+}
+
+template <int J>
+__device__ __forceinline__ void dp_stage(const double *__restrict__ prev, double *__restrict__ cur,
+                                         const double *__restrict__ G, int P, int lane) {
+  const int NB = (P + J - 1) / J;
+  for (int r0 = 0; r0 < NB; r0 += 64) {
+    const int nbr = min(64, NB - r0);
+    const int half = (nbr + 1) >> 1;
+    const int bA = r0 + lane, bB = r0 + nbr - 1 - lane;
+    TileState<J> st;
+    if (lane < half) {
+      st.b = bA;
+      st.kend = bA + 1;
+      st.kstep = 1;
+      st.next_b = (bB > bA) ? bB : -1;
+    } else {
+      st.b = 0;
+      st.kend = -1;
+      st.kstep = 0;
+      st.next_b = -1;
+    }
+    st.kb = 0;
+    double acc[J], A[J], B[J];
+    {
+      const double *ga = G + st.b * J + (J - 1);
+#pragma unroll
+      for (int t = 0; t < J; ++t) {
+        acc[t] = neg_inf();
+        A[t] = ga[-t];
+      }
+    }
+    const int iters = 2 * r0 + nbr + 1;  // (bA+1) + (bB+1) for every folded lane
+    for (int it = 0; it < iters; it += 2) {
+      tile_step<J>(A, B, acc, st, prev, cur, G, P);
+      tile_step<J>(B, A, acc, st, prev, cur, G, P);
+    }
+    if (st.kstep) {  // the last job of this lane has not been flushed by a later step
+      const int rr = st.b * J;
+#pragma unroll
+      for (int t = 0; t < J; ++t)
+        if (rr + t < P) cur[rr + t] = acc[t];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The fused kernel.  J = tile size (rows per lane block), chosen by the host from P (64*J >= P when possible).
+// ------------------------------------------------------------------------------------------------
+template <int J, bool TRACE>
+__global__ void __launch_bounds__(256) place_tiled_kernel(const PlaceParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int oi = blockIdx.x / p.chunks;
+  const int chunk = blockIdx.x - oi * p.chunks;
+  const int o = p.org_list[oi];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int rb = p.rec_begin[o];
+  const int n = p.rec_begin[o + 1] - rb;
+  const int S = p.S;
+  const int sumL = p.sum_len[o];
+  const int P = S - sumL + 1;
+  const int eff = S - sumL + n;
+
+  double *s_pool = reinterpret_cast<double *>(smem_raw);
+  double *s_G = s_pool + p.pool_stride;
+  double *s_rows = s_G + (size_t)(p.max_rec - 1) * p.g_stride;
+  RecDesc *s_rec = reinterpret_cast<RecDesc *>(s_rows + (size_t)nwarps * p.nrows * p.row_stride);
+  unsigned char *s_codes = reinterpret_cast<unsigned char *>(s_rec + p.max_rec);
+
+  // ---- organism prologue: tables into shared memory, gap-energy tables G[c][g] -------------------
+  {
+    const long long pb = p.pool_begin[o];
+    const int pn = (int)(p.pool_begin[o + 1] - pb);
+    for (int i = tid; i < pn; i += blockDim.x) s_pool[i] = __ldg(p.rec_pool + pb + i);
+    if (tid == 0) {
+      int fwd = 0;
+      for (int i = 0; i < n; ++i) {
+        RecDesc d;
+        const char t = p.rec_type[rb + i];
+        d.kind = (t == 'p' || t == 'P') ? 0 : (t == 'm' || t == 'M') ? 1 : (t == 't' || t == 'T') ? 2 : (t == 'r' || t == 'R') ? 3 : 4;
+        d.len = p.rec_len[rb + i];
+        d.nb = p.rec_nb[rb + i];
+        d.data = (int)(p.rec_data[rb + i] - pb);
+        d.fwd = fwd;
+        d.pad = 0;
+        fwd += d.len;
+        s_rec[i] = d;
+      }
+    }
+    const int M = p.con_M[o];
+    const double *D = p.tables + T_DEN;
+    for (int c = 0; c < n - 1; ++c) {
+      const double *pdf = p.con_pool + p.con_begin[o] + (long long)c * (2 * M + 2) + 2;
+      const double auc = __ldg(pdf + (M - 1) + (S - sumL));  // cdf pointer = pdf + max_len, max_len = M-1 (connector.c:3-4)
+      double *Gc = s_G + (size_t)c * p.g_stride;
+      for (int i = tid; i < p.g_stride; i += blockDim.x) {
+        const int g = i - kGPad;
+        Gc[i] = (g < 0 || g >= P) ? neg_inf() : gap_energy(pdf, auc, g, n, eff, D);
+      }
+    }
+  }
+  __syncthreads();
+
+  double *rows = s_rows + (size_t)warp * p.nrows * p.row_stride;
+  unsigned char *codes = s_codes + (size_t)warp * p.code_stride;
+  int err = 0;
+
+  const int first = chunk * p.seqs_per_cta;
+  const int last = min(p.class_count, first + p.seqs_per_cta);
+  for (int si = first + warp; si < last; si += nwarps) {
+    const int seq = p.order[p.class_begin + si];
+    // ---- unpack 2-bit bases (+ unknown mask) into byte codes ------------------------------------
+    {
+      const unsigned *pw = p.packed + p.word_off[seq];
+      const unsigned *uw = p.unk + p.unk_off[seq];
+      for (int b = lane; b < S; b += 32) {
+        const unsigned w = __ldg(pw + (b >> 4));
+        const unsigned u = __ldg(uw + (b >> 5));
+        const unsigned code = (w >> (2 * (b & 15))) & 3u;
+        codes[b] = ((u >> (b & 31)) & 1u) ? 4 : (unsigned char)code;
+      }
+    }
+    __syncwarp();
+
+    // ---- stage 0: C_0 = R_0 (organism.c:381-385) ------------------------------------------------
+    for (int j = lane; j < P; j += 32) rows[j] = score_rec(s_rec[0], s_pool, codes, j, p.tables, err);
+    __syncwarp();
+
+    // ---- stages 1..n-1: C_i[j] = max_k (C_{i-1}[k] + G[j-k]) + R_i[j] (organism.c:347-369) --------
+    for (int i = 1; i < n; ++i) {
+      const double *prev = rows + (size_t)(TRACE ? (i - 1) : ((i - 1) & 1)) * p.row_stride;
+      double *cur = rows + (size_t)(TRACE ? i : (i & 1)) * p.row_stride;
+      const double *Gc = s_G + (size_t)(i - 1) * p.g_stride + kGPad;
+      dp_stage<J>(prev, cur, Gc, P, lane);
+      __syncwarp();
+      const RecDesc rd = s_rec[i];
+      const unsigned char *ci = codes + rd.fwd;
+      for (int j = lane; j < P; j += 32) cur[j] = cur[j] + score_rec(rd, s_pool, ci, j, p.tables, err);
+      __syncwarp();
+    }
+
+    // ---- first maximum of the last row (_aux.c:149-158) ------------------------------------------
+    const double *lastrow = rows + (size_t)(TRACE ? (n - 1) : ((n - 1) & 1)) * p.row_stride;
+    double bv = neg_inf();
+    int bi = 0x7fffffff;
+    for (int j = lane; j < P; j += 32) {
+      const double v = lastrow[j];
+      if (bi == 0x7fffffff || v > bv) { bv = v; bi = j; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+      const int ob = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (ob != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && ob < bi))) { bv = ov; bi = ob; }
+    }
+    const size_t pair = (size_t)o * p.n_seq_total + seq;
+    if (lane == 0) p.E[pair] = bv;
+
+    // ---- traceback (organism.c:398-427): re-scan one column per stage for the first k that reproduces
+    //      the stored value exactly -- identical to the reference's strict '<' update rule -------------
+    if (TRACE) {
+      int m = bi;
+      for (int i = n - 1; i >= 1; --i) {
+        const double *prev = rows + (size_t)(i - 1) * p.row_stride;
+        const double *Gc = s_G + (size_t)(i - 1) * p.g_stride + kGPad;
+        const RecDesc rd = s_rec[i];
+        const double ri = score_rec(rd, s_pool, codes + rd.fwd, m, p.tables, err);
+        const double target = rows[(size_t)i * p.row_stride + m];
+        int found = -1;
+        for (int kb = 0; kb <= m && found < 0; kb += 32) {
+          const int k = kb + lane;
+          const bool hit = (k <= m) && ((prev[k] + Gc[m - k]) + ri == target);
+          const unsigned bal = __ballot_sync(0xffffffffu, hit);
+          if (bal) found = kb + __ffs(bal) - 1;
+        }
+        const int gap = found < 0 ? 0 : m - found;  // nothing ever won: the reference keeps its calloc'ed zeros
+        if (lane == 0) {
+          p.rsc[pair * p.max_rec + i] = ri;
+          p.csc[pair * p.max_rec + i - 1] = found < 0 ? 0.0 : Gc[gap];
+          p.gaps[pair * p.max_rec + i] = gap;
+        }
+        m -= gap;
+      }
+      if (lane == 0) {
+        p.rsc[pair * p.max_rec] = rows[m];
+        p.gaps[pair * p.max_rec] = m;
+      }
+    }
+    __syncwarp();
+  }
+  if (err) atomicOr(p.err_flag, err);
+}

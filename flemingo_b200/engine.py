@@ -131,7 +131,9 @@ class Engine:
         packed = self._packed
         con_begin = packed.con_begin_for_lengths(sset.class_len)
         if packed.con_pool.size != packed.uploaded_con_size:
-            self._upload_packed(packed)  # a rescaled connector variant was appended (rare)
+            # a rescaled connector variant was appended (rare): grow the device pool, keep resident energies
+            _cabi.check(self._lib.fl_update_connectors(self._ctx, _ptr(packed.con_pool), int(packed.con_pool.size)))
+            packed.uploaded_con_size = int(packed.con_pool.size)
         n_org, n_seq, mr = packed.n_org, sset.n_seq, packed.max_rec
         energies = gaps = rsc = csc = None
         if fetch:

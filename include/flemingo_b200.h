@@ -97,6 +97,13 @@ int fl_sequence_classes(fl_ctx *ctx, int set_id, int *n_classes, int *class_len 
 int fl_upload_population(fl_ctx *ctx, const fl_population *pop);
 
 /*
+ * Replaces the connector pool of the uploaded population by a longer one (same base tables, more
+ * adjust_scores variants appended).  Energies already computed stay valid.  The reference rescales a private
+ * copy of the tables inside every get_placement call (organism_object.py:1303,1312-1329).
+ */
+int fl_update_connectors(fl_ctx *ctx, const double *con_pool, long long n_con);
+
+/*
  * Places every organism on every sequence of the set (replaces the loop of
  * OrganismObject.get_binding_energies over get_placement, organism_object.py:958-966,1263-1357, i.e.
  * n_org*n_seq calls of _multiplacement.calculate, _interface.c:45).
