@@ -13,6 +13,7 @@ LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libflemingo_b200.so"
 FL_OK = 0
 FL_E_CUDA, FL_E_ARG, FL_E_TOO_LARGE, FL_E_NAN_NULL, FL_E_UNSUPPORTED, FL_E_STATE = -1, -2, -3, -4, -5, -6
 FL_WANT_TRACE = 1
+FL_EXACT_ONLY = 2
 FL_MAX_SETS = 8
 FIT_METHODS = {"Welch": 0, "Yuen": 1, "Trim-left-M": 2, "Trim-left-M-SD": 3}
 

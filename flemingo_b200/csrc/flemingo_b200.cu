@@ -49,6 +49,7 @@ static int fail(int code, const char *fmt, ...) {
   } while (0)
 
 #include "place_kernel.cuh"
+#include "place_fast_kernel.cuh"
 #include "fitness_kernel.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -67,6 +68,42 @@ static int pick_tile(int P) {
   for (int j = 0; j < kNumTileSizes; ++j)
     if (64 * kTileSizes[j] >= P) return j;
   return kNumTileSizes - 1;
+}
+
+// Integer fast path: (tile size J, lanes per pair TEAM).  A team covers 2*TEAM*J offsets per folded round.
+typedef void (*fast_kernel_fn)(const FastParams);
+struct FastConfig {
+  int J, team;
+  fast_kernel_fn fn;
+};
+#define FAST_CFG(J, T) {J, T, place_fast_kernel<J, T>}
+static const FastConfig kFastConfigs[] = {
+    FAST_CFG(3, 8),  FAST_CFG(5, 8),  FAST_CFG(7, 8),  FAST_CFG(9, 8),  FAST_CFG(11, 8), FAST_CFG(13, 8), FAST_CFG(15, 8),
+    FAST_CFG(17, 8), FAST_CFG(19, 8), FAST_CFG(21, 8), FAST_CFG(13, 16), FAST_CFG(15, 16), FAST_CFG(17, 16), FAST_CFG(19, 16),
+    FAST_CFG(21, 16), FAST_CFG(13, 32), FAST_CFG(17, 32), FAST_CFG(21, 32)};
+constexpr int kNumFastConfigs = (int)(sizeof(kFastConfigs) / sizeof(kFastConfigs[0]));
+
+// Estimated issue slots per pair: tiles x (J*J cells + loads and bookkeeping), scaled by the share of the warp a team uses.
+static double fast_cost(int P, int J, int team) {
+  const int NB = (P + J - 1) / J;
+  double tiles = 0;
+  for (int r0 = 0; r0 < NB; r0 += 2 * team) {
+    const int nbr = std::min(2 * team, NB - r0);
+    tiles += (2 * r0 + nbr + 2) & ~1;
+  }
+  return tiles * (J * J + 3.0 * J + 24.0) * team / 32.0;
+}
+static int pick_fast(int P) {
+  int best = 0;
+  double best_cost = 1e300;
+  for (int i = 0; i < kNumFastConfigs; ++i) {
+    const double c = fast_cost(P, kFastConfigs[i].J, kFastConfigs[i].team);
+    if (c < best_cost) {
+      best_cost = c;
+      best = i;
+    }
+  }
+  return best;
 }
 struct DevBuf {
   void *p = nullptr;
@@ -98,7 +135,7 @@ struct SeqSet {
   bool valid = false;
   int n_seq = 0;
   std::vector<SeqClass> classes;
-  DevBuf packed, unk, word_off, unk_off, order;
+  DevBuf packed, unk, word_off, unk_off, order, has_unk;
   DevBuf E;  // energies [n_org][n_seq]
   int E_n_org = 0;
   bool E_valid = false;
@@ -108,6 +145,7 @@ struct Population {
   bool valid = false;
   int n_org = 0, n_rec_total = 0, max_rec = 0;
   std::vector<int> rec_begin, sum_len, con_M, pool_len;
+  std::vector<int> kmer_need;  // ints of 4-mer tables if the organism is PSSM-only with >= 2 recognizers, else -1
   long long n_con = 0;
   int max_pool = 0, min_sum_len = 0;
   DevBuf d_rec_begin, d_rec_type, d_rec_len, d_rec_nb, d_rec_data, d_pool_begin, d_rec_pool, d_con_M, d_con_pool, d_sum_len;
@@ -116,7 +154,8 @@ struct Population {
 struct fl_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  DevBuf tables, err_flag, con_begin, org_list, gaps, rsc, csc, fit_out, fit_scratch;
+  DevBuf tables, err_flag, con_begin, org_list, gaps, rsc, csc, fit_out, fit_scratch, fb_count, fb_pairs;
+  long long fast_pairs = 0, fallback_pairs = 0;  // statistics of the last fl_place_batch
   Population pop, scratch_pop;
   SeqSet sets[FL_MAX_SETS + 1];  // the extra slot serves fl_calculate
   long long launches = 0;
@@ -141,6 +180,7 @@ extern "C" int fl_ctx_create(int device, const double *tables, long long n_table
   }
   int rc = ctx->tables.ensure(sizeof(double) * FL_N_TABLE_DOUBLES);
   if (rc == FL_OK) rc = ctx->err_flag.ensure(sizeof(int));
+  if (rc == FL_OK) rc = ctx->fb_count.ensure(sizeof(int));
   if (rc != FL_OK) {
     delete ctx;
     return rc;
@@ -152,6 +192,10 @@ extern "C" int fl_ctx_create(int device, const double *tables, long long n_table
     CK(cudaFuncSetAttribute(kPlaceKernels[j][0], cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     CK(cudaFuncSetAttribute(kPlaceKernels[j][1], cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   }
+  for (int j = 0; j < kNumFastConfigs; ++j)
+    CK(cudaFuncSetAttribute(kFastConfigs[j].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+  CK(cudaFuncSetAttribute(place_list_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+  CK(cudaFuncSetAttribute(place_list_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   *out = ctx;
   return FL_OK;
 }
@@ -167,11 +211,11 @@ extern "C" int fl_ctx_destroy(fl_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (SeqSet &s : ctx->sets) {
-    s.packed.release(); s.unk.release(); s.word_off.release(); s.unk_off.release(); s.order.release(); s.E.release();
+    s.packed.release(); s.unk.release(); s.word_off.release(); s.unk_off.release(); s.order.release(); s.has_unk.release(); s.E.release();
   }
   release_pop(ctx->pop);
   release_pop(ctx->scratch_pop);
-  DevBuf *bufs[] = {&ctx->tables, &ctx->err_flag, &ctx->con_begin, &ctx->org_list, &ctx->gaps, &ctx->rsc, &ctx->csc, &ctx->fit_out, &ctx->fit_scratch};
+  DevBuf *bufs[] = {&ctx->tables, &ctx->err_flag, &ctx->con_begin, &ctx->org_list, &ctx->gaps, &ctx->rsc, &ctx->csc, &ctx->fit_out, &ctx->fit_scratch, &ctx->fb_count, &ctx->fb_pairs};
   for (DevBuf *b : bufs) b->release();
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -213,6 +257,7 @@ static inline int base_code(char c) {
 static int upload_sequences(fl_ctx *ctx, SeqSet &set, const char *bytes, const long long *offsets, int n_seq) {
   if (n_seq < 0 || (n_seq > 0 && (!bytes || !offsets))) return fail(FL_E_ARG, "fl_upload_sequences: bad arguments");
   std::vector<int> len(n_seq), word_off(n_seq), unk_off(n_seq), order(n_seq);
+  std::vector<unsigned char> has_unk((size_t)n_seq + 1, 0);
   long long words = 0, uwords = 0;
   for (int s = 0; s < n_seq; ++s) {
     const long long l = offsets[s + 1] - offsets[s];
@@ -232,7 +277,10 @@ static int upload_sequences(fl_ctx *ctx, SeqSet &set, const char *bytes, const l
     unsigned *uw = unk.data() + unk_off[s];
     for (int i = 0; i < len[s]; ++i) {
       const int c = base_code(b[i]);
-      if (c < 0) uw[i >> 5] |= 1u << (i & 31);
+      if (c < 0) {
+        uw[i >> 5] |= 1u << (i & 31);
+        has_unk[s] = 1;
+      }
       else pw[i >> 4] |= (unsigned)c << (2 * (i & 15));
     }
   }
@@ -247,7 +295,7 @@ static int upload_sequences(fl_ctx *ctx, SeqSet &set, const char *bytes, const l
   int rc;
   if ((rc = set.packed.ensure(packed.size() * 4)) || (rc = set.unk.ensure(unk.size() * 4)) ||
       (rc = set.word_off.ensure((size_t)n_seq * 4 + 4)) || (rc = set.unk_off.ensure((size_t)n_seq * 4 + 4)) ||
-      (rc = set.order.ensure((size_t)n_seq * 4 + 4)))
+      (rc = set.order.ensure((size_t)n_seq * 4 + 4)) || (rc = set.has_unk.ensure((size_t)n_seq + 4)))
     return rc;
   CK(cudaMemcpyAsync(set.packed.p, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(set.unk.p, unk.data(), unk.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -255,6 +303,7 @@ static int upload_sequences(fl_ctx *ctx, SeqSet &set, const char *bytes, const l
     CK(cudaMemcpyAsync(set.word_off.p, word_off.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(set.unk_off.p, unk_off.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(set.order.p, order.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(set.has_unk.p, has_unk.data(), (size_t)n_seq, cudaMemcpyHostToDevice, ctx->stream));
   }
   CK(cudaStreamSynchronize(ctx->stream));  // the staging vectors die at return
   set.valid = true;
@@ -288,6 +337,7 @@ static int upload_population(fl_ctx *ctx, Population &P, const fl_population *po
   P.sum_len.assign(n_org, 0);
   P.con_M.assign(pop->con_M, pop->con_M + n_org);
   P.pool_len.assign(n_org, 0);
+  P.kmer_need.assign(n_org, -1);
   P.max_rec = 0;
   P.max_pool = 0;
   P.min_sum_len = 0x7fffffff;
@@ -312,6 +362,16 @@ static int upload_population(fl_ctx *ctx, Population &P, const fl_population *po
     }
     P.sum_len[o] = sl;
     P.pool_len[o] = (int)(pop->pool_begin[o + 1] - pop->pool_begin[o]);
+    {
+      int need = 0;
+      bool all_pssm = n >= 2;
+      for (int i = 0; i < n && all_pssm; ++i) {
+        const char t = pop->rec_type[rb + i];
+        all_pssm = (t == 'p' || t == 'P');
+        need += 256 * ((pop->rec_len[rb + i] + 3) / 4);
+      }
+      P.kmer_need[o] = all_pssm ? need : -1;
+    }
     P.max_rec = std::max(P.max_rec, n);
     P.max_pool = std::max(P.max_pool, P.pool_len[o]);
     P.min_sum_len = std::min(P.min_sum_len, sl);
@@ -457,25 +517,75 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
     }
     if (smem > (size_t)kMaxSmem)
       return fail(FL_E_UNSUPPORTED, "placement of %d offsets x %d recognizers needs %zu bytes of shared memory (limit %d)", Pmax, P.max_rec, smem, kMaxSmem);
-    // organisms are bucketed by tile size (a compile-time constant of the kernel); one launch per bucket
-    std::vector<int> bucket[kNumTileSizes];
-    for (int o = 0; o < n_org; ++o) bucket[pick_tile(cl.len - P.sum_len[o] + 1)].push_back(o);
+    // ---- buckets: integer fast path (PSSM-only organisms, P >= 2) by (J, TEAM); everything else exact by J ----
+    const bool allow_fast = !(flags & FL_EXACT_ONLY);
+    FastParams fp;
+    fp.gq_stride = kGPad + Pmax + kGPad;
+    fp.rowq_stride = (Pmax + kMaxJ + 4) & ~3;
+    fp.seqw_stride = (cl.len + 15) / 16 + 3;
+    fp.bitmap_words = (Pmax + 31) / 32 + 1;
+    fp.want_trace = trace ? 1 : 0;
+    fp.has_unk = set.has_unk.as<unsigned char>();
+    int kmer_cap = 0;
+    std::vector<int> exact_bucket[kNumTileSizes], fast_bucket[kNumFastConfigs];
+    long long n_fast_org = 0;
+    for (int o = 0; o < n_org; ++o) {
+      const int Po = cl.len - P.sum_len[o] + 1;
+      if (allow_fast && P.kmer_need[o] > 0 && P.kmer_need[o] <= 16384 && Po >= 2) {
+        fast_bucket[pick_fast(Po)].push_back(o);
+        kmer_cap = std::max(kmer_cap, P.kmer_need[o]);
+        ++n_fast_org;
+      } else {
+        exact_bucket[pick_tile(Po)].push_back(o);
+      }
+    }
+    fp.kmer_cap = kmer_cap;
+    // fast-path geometry; if even one warp per CTA does not fit, those organisms go to the exact kernel
+    int fast_warps[kNumFastConfigs];
+    size_t fast_smem[kNumFastConfigs];
+    for (int j = 0; j < kNumFastConfigs; ++j) {
+      fast_warps[j] = 0;
+      fast_smem[j] = 0;
+      if (fast_bucket[j].empty()) continue;
+      const int team = kFastConfigs[j].team, nt = 32 / team;
+      const int slot = (((P.max_rec * fp.rowq_stride) + 31) & ~31) + (team & 31);
+      for (int nw = 4; nw >= 1; nw >>= 1) {
+        const size_t d = (size_t)pp.pool_stride + (size_t)(P.max_rec - 1) * pp.g_stride + 2ull * nw * P.max_rec * kCandCap;
+        const size_t i = (size_t)(P.max_rec - 1) * fp.gq_stride + fp.kmer_cap + (size_t)nw * nt * slot + (size_t)nw * nt * fp.seqw_stride +
+                         2ull * nw * P.max_rec * kCandCap + (size_t)nw * P.max_rec + (size_t)nw * fp.bitmap_words;
+        const size_t bytes = d * 8 + i * 4 + sizeof(RecDesc) * P.max_rec + sizeof(FastPlan) + 16;
+        if (bytes <= (size_t)kMaxSmem) {
+          fast_warps[j] = nw;
+          fast_smem[j] = bytes;
+          break;
+        }
+      }
+      if (!fast_warps[j]) {
+        for (int o : fast_bucket[j]) exact_bucket[pick_tile(cl.len - P.sum_len[o] + 1)].push_back(o);
+        n_fast_org -= (long long)fast_bucket[j].size();
+        fast_bucket[j].clear();
+      }
+    }
     std::vector<int> list;
     list.reserve(n_org);
-    int begin_of[kNumTileSizes];
+    int exact_begin[kNumTileSizes], fast_begin[kNumFastConfigs];
     for (int j = 0; j < kNumTileSizes; ++j) {
-      begin_of[j] = (int)list.size();
-      list.insert(list.end(), bucket[j].begin(), bucket[j].end());
+      exact_begin[j] = (int)list.size();
+      list.insert(list.end(), exact_bucket[j].begin(), exact_bucket[j].end());
+    }
+    for (int j = 0; j < kNumFastConfigs; ++j) {
+      fast_begin[j] = (int)list.size();
+      list.insert(list.end(), fast_bucket[j].begin(), fast_bucket[j].end());
     }
     int *d_list = ctx->org_list.as<int>() + (size_t)c * n_org;
     CK(cudaMemcpyAsync(d_list, list.data(), (size_t)n_org * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const long long target_ctas = (long long)n_sm * 16;
     for (int j = 0; j < kNumTileSizes; ++j) {
-      const int n_b = (int)bucket[j].size();
+      const int n_b = (int)exact_bucket[j].size();
       if (!n_b) continue;
-      pp.org_list = d_list + begin_of[j];
+      pp.org_list = d_list + exact_begin[j];
       // chunking: enough CTAs to fill the machine a few times over, at least one sequence per warp
       const long long pairs = (long long)n_b * cl.count;
-      const long long target_ctas = (long long)n_sm * 16;
       int spc = (int)std::max<long long>(nwarps, (pairs + target_ctas - 1) / target_ctas);
       spc = std::min(spc, std::max(nwarps, 64));
       spc = ((spc + nwarps - 1) / nwarps) * nwarps;
@@ -484,6 +594,45 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
       const long long grid = (long long)n_b * pp.chunks;
       if (grid > 0x7fffffffLL) return fail(FL_E_UNSUPPORTED, "grid too large");
       kPlaceKernels[j][trace ? 1 : 0]<<<(unsigned)grid, nwarps * 32, smem, ctx->stream>>>(pp);
+      CK(cudaGetLastError());
+      ctx->launches++;
+    }
+    if (n_fast_org > 0) {
+      const long long cap = n_fast_org * cl.count;
+      if ((rc = ctx->fb_pairs.ensure((size_t)cap * sizeof(int2)))) return rc;
+      fp.fb_count = ctx->fb_count.as<int>();
+      fp.fb_pairs = ctx->fb_pairs.as<int2>();
+      fp.fb_cap = (int)std::min<long long>(cap, 0x7fffffffLL);
+      CK(cudaMemsetAsync(ctx->fb_count.p, 0, sizeof(int), ctx->stream));
+      for (int j = 0; j < kNumFastConfigs; ++j) {
+        const int n_b = (int)fast_bucket[j].size();
+        if (!n_b) continue;
+        const int team = kFastConfigs[j].team, nt = 32 / team, nw = fast_warps[j];
+        fp.slotq_stride = (((P.max_rec * fp.rowq_stride) + 31) & ~31) + (team & 31);
+        const int per_round = nw * nt;
+        const long long pairs = (long long)n_b * cl.count;
+        int spc = (int)std::max<long long>(per_round, (pairs + target_ctas - 1) / target_ctas);
+        spc = std::min(spc, std::max(per_round, 128));
+        spc = ((spc + per_round - 1) / per_round) * per_round;
+        fp.base = pp;
+        fp.base.org_list = d_list + fast_begin[j];
+        fp.base.seqs_per_cta = spc;
+        fp.base.chunks = (cl.count + spc - 1) / spc;
+        const long long grid = (long long)n_b * fp.base.chunks;
+        if (grid > 0x7fffffffLL) return fail(FL_E_UNSUPPORTED, "grid too large");
+        kFastConfigs[j].fn<<<(unsigned)grid, nw * 32, fast_smem[j], ctx->stream>>>(fp);
+        CK(cudaGetLastError());
+        ctx->launches++;
+      }
+      // the pairs the integer pass declined, by the exact kernel in list mode (one warp per CTA)
+      PlaceParams lp = pp;
+      const size_t lsmem = 8ull * ((size_t)lp.pool_stride + (size_t)(P.max_rec - 1) * lp.g_stride + (size_t)lp.nrows * lp.row_stride) +
+                           sizeof(RecDesc) * P.max_rec + (size_t)lp.code_stride;
+      const unsigned lgrid = (unsigned)std::min<long long>(cap, (long long)n_sm * 16);
+      if (trace)
+        place_list_kernel<true><<<lgrid, 32, lsmem, ctx->stream>>>(lp, fp.fb_count, fp.fb_pairs);
+      else
+        place_list_kernel<false><<<lgrid, 32, lsmem, ctx->stream>>>(lp, fp.fb_count, fp.fb_pairs);
       CK(cudaGetLastError());
       ctx->launches++;
     }

@@ -1,0 +1,477 @@
+// place_fast_kernel.cuh -- filter-and-refine placement: an int32 fixed-point DPX pass finds, with a rigorous
+// error bound, every DP cell that can lie on the optimal path; those few cells are then re-evaluated in exact
+// IEEE double in the reference's operand order.  Results are bit-identical to the reference; pairs for which
+// the candidate sets grow too large (massive ties) or that the fixed-point range cannot hold are pushed to a
+// device-side list and placed by the exact kernel (place_list_kernel).
+//
+// Why it is exact.  Let C be the reference's doubles (organism.c:347-369), Chat the same sums in real
+// arithmetic (|C - Chat| < 2^-30 units after scaling, see `slack`), and Cq the integer pass with every table
+// entry rounded to the nearest integer in units of 1/s (s a power of two, so scaling itself is exact):
+//     |Cq_i[j] - s*Chat_i[j]| <= err_i = 0.5 * (number of rounded table entries on a path up to stage i).
+// Therefore every j that maximises C_{n-1} has Cq_{n-1}[j] >= max Cq_{n-1} - 2 err_{n-1} - slack, and every k
+// that can win cell (i, j) has Cq_{i-1}[k] + Gq[j-k] >= (Cq_i[j] - Rq_i[j]) - 2 (err_{i-1} + 0.5) - slack.
+// Walking these inequalities down from the last row yields per-stage candidate sets F_i; evaluating
+//     C_i[j] = max_{k in F_{i-1}, k <= j} fl(fl(C_{i-1}[k] + G[j-k]) + R_i[j])   (ascending k, strict <)
+// on them reproduces the reference values AND its first-k / first-j tie rule.  The sentinel that stands for the
+// reference's -1e10 (gap P-1) and for out-of-triangle cells is chosen below (min path - max path - threshold),
+// so a path through it can never enter a candidate set nor overflow int32.
+//
+// PSSM score rows in the integer pass use 4-mer lookup tables (256 entries per group of 4 columns, rounded ONCE
+// per entry), so a row costs ceil(L/4) lookups per offset instead of L adds; integer addition is associative,
+// which makes this legal here and illegal in the exact pass.
+#pragma once
+
+constexpr int kCandCap = 16;   // candidates kept per stage before a pair is handed to the exact kernel
+constexpr int kSlackUnits = 2; // covers fp64-vs-real rounding of the reference sums (<< 1 unit) with margin
+
+struct FastParams {
+  PlaceParams base;
+  const unsigned char *has_unk;  // [n_seq] sequence holds a non-ACGT byte -> exact kernel
+  int *fb_count;
+  int2 *fb_pairs;
+  int fb_cap;
+  int gq_stride;     // ints per quantised connector table (kGPad + Pmax + kGPad)
+  int rowq_stride;   // ints per quantised row
+  int slotq_stride;  // ints per pair slot (max_rec rows), == TEAM (mod 32) so that teams hit disjoint banks
+  int seqw_stride;   // u32 words per packed sequence copy
+  int kmer_cap;      // ints available for the 4-mer tables of one organism
+  int bitmap_words;  // u32 words of the per-warp candidate bitmap
+  int want_trace;
+};
+
+struct FastPlan {
+  double scale;                          // s: quantised = rint(value * s)
+  int sent;                              // sentinel ("minus infinity" of the integer pass)
+  int ok;                                // 0: this organism cannot use the integer pass
+  int thr_final;                         // slack on the last row
+  int thr_pred[FL_MAX_RECOGNIZERS];      // slack on predecessor scans of stage i
+  int ngroups[FL_MAX_RECOGNIZERS];       // 4-mer groups of recognizer i
+  int kmer_off[FL_MAX_RECOGNIZERS];      // offset of its tables in s_kmer
+};
+
+struct FastSmem {
+  double *pool, *G, *cv, *cr;
+  int *Gq, *kmer, *rowsq, *cj, *ca, *cn;
+  unsigned *seqw, *bitmap;
+  RecDesc *rec;
+  FastPlan *plan;
+};
+
+__device__ __forceinline__ size_t fast_smem_bytes_dev(const FastParams &f, int nwarps, int nt) {
+  const PlaceParams &p = f.base;
+  size_t d = (size_t)p.pool_stride + (size_t)(p.max_rec - 1) * p.g_stride + 2ull * nwarps * p.max_rec * kCandCap;
+  size_t i = (size_t)(p.max_rec - 1) * f.gq_stride + f.kmer_cap + (size_t)nwarps * nt * f.slotq_stride +
+             (size_t)nwarps * nt * f.seqw_stride + 2ull * nwarps * p.max_rec * kCandCap + (size_t)nwarps * p.max_rec +
+             (size_t)nwarps * f.bitmap_words;
+  return d * 8 + i * 4 + sizeof(RecDesc) * p.max_rec + sizeof(FastPlan);
+}
+
+__device__ __forceinline__ FastSmem carve_fast(const FastParams &f, unsigned char *raw, int nwarps, int nt) {
+  const PlaceParams &p = f.base;
+  FastSmem s;
+  s.pool = reinterpret_cast<double *>(raw);
+  s.G = s.pool + p.pool_stride;
+  s.cv = s.G + (size_t)(p.max_rec - 1) * p.g_stride;
+  s.cr = s.cv + (size_t)nwarps * p.max_rec * kCandCap;
+  s.plan = reinterpret_cast<FastPlan *>(s.cr + (size_t)nwarps * p.max_rec * kCandCap);
+  s.rec = reinterpret_cast<RecDesc *>(s.plan + 1);
+  s.Gq = reinterpret_cast<int *>(s.rec + p.max_rec);
+  s.kmer = s.Gq + (size_t)(p.max_rec - 1) * f.gq_stride;
+  s.rowsq = s.kmer + f.kmer_cap;
+  s.seqw = reinterpret_cast<unsigned *>(s.rowsq + (size_t)nwarps * nt * f.slotq_stride);
+  s.cj = reinterpret_cast<int *>(s.seqw + (size_t)nwarps * nt * f.seqw_stride);
+  s.ca = s.cj + (size_t)nwarps * p.max_rec * kCandCap;
+  s.cn = s.ca + (size_t)nwarps * p.max_rec * kCandCap;
+  s.bitmap = reinterpret_cast<unsigned *>(s.cn + (size_t)nwarps * p.max_rec);
+  return s;
+}
+
+// ---- warp reductions -------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_min_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_max_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// base code (0..3) at position pos of a packed copy (16 bases per word, LSB first)
+__device__ __forceinline__ int packed_code(const unsigned *w, int pos) { return (w[pos >> 4] >> (2 * (pos & 15))) & 3; }
+
+// quantised PSSM score at `pos` (already including the recognizer's forward offset): one 4-mer lookup per group
+__device__ __forceinline__ int score_q(const int *__restrict__ tab, int ngroups, const unsigned *__restrict__ w, int pos) {
+  int v = 0;
+  for (int g = 0; g < ngroups; ++g) {
+    const int q = pos + 4 * g;
+    const unsigned kmer = __funnelshift_r(w[q >> 4], w[(q >> 4) + 1], 2 * (q & 15)) & 0xffu;
+    v += tab[256 * g + kmer];
+  }
+  return v;
+}
+
+// exact PSSM score (recognizer.c:130-168) from the packed copy; the fast path only sees ACGT sequences
+__device__ __forceinline__ double score_exact_packed(const RecDesc &r, const double *s_pool, const unsigned *w, int pos) {
+  const double *m = s_pool + r.data;
+  double s = 0.0;
+  for (int col = 0; col < r.len; ++col) s += m[4 * col + packed_code(w, pos + col)];
+  return s;
+}
+
+// ---- quantisation plan of one organism (executed by warp 0 after the exact tables are in shared memory) ----
+__device__ void build_fast_plan(const FastParams &f, const OrgView &v, const FastSmem &sm, int lane) {
+  const PlaceParams &p = f.base;
+  FastPlan *plan = sm.plan;
+  const int n = v.n, P = v.P;
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  // (1) value ranges in doubles
+  double lo_sum = 0.0, hi_sum = 0.0, range = 0.0, g_lo_min = 0.0;
+  int kmer_need = 0;
+  bool bad = false;  // NaN anywhere in the tables
+  for (int r = 0; r < n; ++r) {
+    const RecDesc rd = sm.rec[r];
+    const double *m = sm.pool + rd.data;
+    double lo = 0.0, hi = 0.0;
+    for (int c = lane; c < rd.len; c += 32) {
+      lo += fmin(fmin(m[4 * c], m[4 * c + 1]), fmin(m[4 * c + 2], m[4 * c + 3]));
+      hi += fmax(fmax(m[4 * c], m[4 * c + 1]), fmax(m[4 * c + 2], m[4 * c + 3]));
+      bad |= (m[4 * c] != m[4 * c]) | (m[4 * c + 1] != m[4 * c + 1]) | (m[4 * c + 2] != m[4 * c + 2]) | (m[4 * c + 3] != m[4 * c + 3]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo += __shfl_xor_sync(0xffffffffu, lo, o);
+      hi += __shfl_xor_sync(0xffffffffu, hi, o);
+    }
+    lo_sum += lo;
+    hi_sum += hi;
+    range += hi - lo;
+    kmer_need += 256 * ((rd.len + 3) >> 2);
+  }
+  for (int c = 0; c < n - 1; ++c) {
+    const double *Gc = sm.G + (size_t)c * p.g_stride + kGPad;
+    double lo = inf, hi = -inf;
+    for (int g = lane; g <= P - 2; g += 32) {  // legit gaps; g = P-1 is the reference's -1e10 sentinel
+      lo = fmin(lo, Gc[g]);
+      hi = fmax(hi, Gc[g]);
+      bad |= (Gc[g] != Gc[g]);
+    }
+    lo = warp_min(lo);
+    hi = warp_max(hi);
+    lo_sum += lo;
+    hi_sum += hi;
+    range += hi - lo;
+    g_lo_min = fmin(g_lo_min, lo);
+  }
+  bad = __any_sync(0xffffffffu, bad);
+  // (2) scale: everything, including (n-1) sentinels of size ~range, must stay inside +-2^30
+  // the sentinel sits below the lowest legit gap energy by more than the whole value range (see below), and up
+  // to n-1 of them can add up on a (never selected) path
+  const double need = fabs(lo_sum) + fabs(hi_sum) + (double)n * (range + fabs(g_lo_min) + 2.0) + 2.0;
+  int ok = !bad && (P >= 2) && (need == need) && (need < 1.0e9) && (kmer_need <= f.kmer_cap);
+  int e = 0;
+  if (ok) {
+    e = ilogb(1073741824.0 / need) - 1;
+    if (e > 40) e = 40;
+    if (e < 0) ok = 0;
+  }
+  const double s = ok ? scalbn(1.0, e) : 1.0;
+  // (3) quantised tables, their integer ranges, thresholds
+  long long lo_q = 0, hi_q = 0, lo_q_rec = 0;
+  int groups_total = 0, off = 0, g_lo_q = 0;
+  if (ok) {
+    for (int r = 0; r < n; ++r) {
+      const RecDesc rd = sm.rec[r];
+      const double *m = sm.pool + rd.data;
+      const int ng = (rd.len + 3) >> 2;
+      if (lane == 0) {
+        plan->ngroups[r] = ng;
+        plan->kmer_off[r] = off;
+      }
+      for (int g = 0; g < ng; ++g) {
+        int lo = 0x7fffffff, hi = -0x7fffffff;
+        for (int kmer = lane; kmer < 256; kmer += 32) {
+          double acc = 0.0;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int col = 4 * g + t;
+            if (col < rd.len) acc += m[4 * col + ((kmer >> (2 * t)) & 3)];
+          }
+          const int q = __double2int_rn(acc * s);
+          sm.kmer[off + 256 * g + kmer] = q;
+          lo = min(lo, q);
+          hi = max(hi, q);
+        }
+        lo_q += warp_min_i(lo);
+        hi_q += warp_max_i(hi);
+      }
+      off += 256 * ng;
+      groups_total += ng;
+    }
+    lo_q_rec = lo_q;
+    for (int c = 0; c < n - 1; ++c) {
+      const double *Gc = sm.G + (size_t)c * p.g_stride + kGPad;
+      int lo = 0x7fffffff, hi = -0x7fffffff;
+      for (int g = lane; g <= P - 2; g += 32) {
+        const int q = __double2int_rn(Gc[g] * s);
+        lo = min(lo, q);
+        hi = max(hi, q);
+      }
+      lo = warp_min_i(lo);
+      lo_q += lo;
+      hi_q += warp_max_i(hi);
+      g_lo_q = min(g_lo_q, lo);
+    }
+  }
+  const long long range_q = hi_q - lo_q;
+  const int thr_max = groups_total + n + 2 * kSlackUnits + 2;
+  // sentinel: below the lowest legit gap energy by more than (range of any path) + (largest threshold), so a path
+  // through it is below EVERY legit path of the same stage by more than any threshold
+  const long long sent = (long long)g_lo_q - (range_q + thr_max + 4);
+  if (ok && (lo_q_rec + (long long)(n - 1) * sent < -2000000000LL || hi_q > 2000000000LL || lo_q < -2000000000LL)) ok = 0;
+  if (ok) {
+    for (int c = 0; c < n - 1; ++c) {
+      const double *Gc = sm.G + (size_t)c * p.g_stride + kGPad;
+      int *Gq = sm.Gq + (size_t)c * f.gq_stride;
+      for (int i = lane; i < f.gq_stride; i += 32) {
+        const int g = i - kGPad;
+        Gq[i] = (g >= 0 && g <= P - 2) ? __double2int_rn(Gc[g] * s) : (int)sent;
+      }
+    }
+  }
+  if (lane == 0) {
+    plan->scale = s;
+    plan->sent = (int)sent;
+    plan->ok = ok;
+    // err_i (in half units) = groups of recognizers 0..i + i connectors
+    int half_units = 0;
+    for (int i = 0; i < n; ++i) {
+      // predecessors of stage i: values Cq_{i-1}[k] + Gq  ->  err_{i-1} + 0.5
+      plan->thr_pred[i] = half_units + 1 + 2 * kSlackUnits;   // 2 * (err_{i-1} + 0.5) = half_units + 1   (i >= 1)
+      half_units += plan->ngroups[i] + (i > 0 ? 1 : 0);
+    }
+    plan->thr_final = half_units + 2 * kSlackUnits;          // 2 * err_{n-1}
+  }
+}
+
+// ---- exact refinement of one pair on its candidate sets (whole warp) -----------------------------------
+// rowsq: the pair's quantised rows [n][rowq_stride]; w: its packed sequence.  Returns false if a candidate set
+// overflowed (pair goes to the exact kernel).
+__device__ bool refine_pair(const FastParams &f, const OrgView &v, const FastSmem &sm, const int *rowsq, const unsigned *w,
+                            int seq, int warp, int lane) {
+  const PlaceParams &p = f.base;
+  const FastPlan &plan = *sm.plan;
+  const int n = v.n, P = v.P;
+  int *cj = sm.cj + (size_t)warp * p.max_rec * kCandCap;
+  int *ca = sm.ca + (size_t)warp * p.max_rec * kCandCap;
+  int *cn = sm.cn + (size_t)warp * p.max_rec;
+  double *cv = sm.cv + (size_t)warp * p.max_rec * kCandCap;
+  double *cr = sm.cr + (size_t)warp * p.max_rec * kCandCap;
+  unsigned *bitmap = sm.bitmap + (size_t)warp * f.bitmap_words;
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  // (1) candidates on the last row
+  {
+    const int *row = rowsq + (size_t)(n - 1) * f.rowq_stride;
+    int mx = -0x7fffffff;
+    for (int j = lane; j < P; j += 32) mx = max(mx, row[j]);
+    mx = warp_max_i(mx);
+    const int thr = mx - plan.thr_final;
+    int count = 0;
+    for (int base = 0; base < P; base += 32) {
+      const int j = base + lane;
+      const bool pred = (j < P) && (row[j] >= thr);
+      const unsigned bal = __ballot_sync(0xffffffffu, pred);
+      if (pred) {
+        const int idx = count + __popc(bal & lt_mask);
+        if (idx < kCandCap) cj[(n - 1) * kCandCap + idx] = j;
+      }
+      count += __popc(bal);
+    }
+    if (count > kCandCap) return false;
+    if (lane == 0) cn[n - 1] = count;
+  }
+  __syncwarp();
+  // (2) candidate sets of the earlier stages, top down
+  const int words = (P + 31) >> 5;
+  for (int i = n - 1; i >= 1; --i) {
+    for (int t = lane; t < words; t += 32) bitmap[t] = 0u;
+    __syncwarp();
+    const int *prev = rowsq + (size_t)(i - 1) * f.rowq_stride;
+    const int *cur = rowsq + (size_t)i * f.rowq_stride;
+    const int *Gq = sm.Gq + (size_t)(i - 1) * f.gq_stride + kGPad;
+    const int *tab = sm.kmer + plan.kmer_off[i];
+    const int fwd = sm.rec[i].fwd;
+    const int cnt = cn[i];
+    for (int c = 0; c < cnt; ++c) {
+      const int j = cj[i * kCandCap + c];
+      const int thr = (cur[j] - score_q(tab, plan.ngroups[i], w, fwd + j)) - plan.thr_pred[i];
+      for (int base = 0; base <= j; base += 32) {
+        const int k = base + lane;
+        const bool pred = (k <= j) && (prev[k] + Gq[j - k] >= thr);
+        const unsigned bal = __ballot_sync(0xffffffffu, pred);
+        if (lane == 0 && bal) bitmap[base >> 5] |= bal;
+      }
+      __syncwarp();
+    }
+    int count = 0;
+    for (int base = 0; base < P; base += 32) {
+      const unsigned word = bitmap[base >> 5];
+      const bool pred = (word >> lane) & 1u;
+      if (pred) {
+        const int idx = count + __popc(word & lt_mask);
+        if (idx < kCandCap) cj[(i - 1) * kCandCap + idx] = base + lane;
+      }
+      count += __popc(word);
+    }
+    if (count > kCandCap) return false;
+    if (lane == 0) cn[i - 1] = count;
+    __syncwarp();
+  }
+  // (3) exact forward evaluation on the candidate sets (lane = one candidate of the stage)
+  if (lane < cn[0]) {
+    const double r0 = score_exact_packed(sm.rec[0], sm.pool, w, cj[lane]);
+    cv[lane] = r0;
+    cr[lane] = r0;
+  }
+  __syncwarp();
+  for (int i = 1; i < n; ++i) {
+    if (lane < cn[i]) {
+      const int j = cj[i * kCandCap + lane];
+      const RecDesc rd = sm.rec[i];
+      const double rj = score_exact_packed(rd, sm.pool, w, rd.fwd + j);
+      const double *G = sm.G + (size_t)(i - 1) * p.g_stride + kGPad;
+      double best = neg_inf();
+      int arg = -1;
+      const int np = cn[i - 1];
+      for (int d = 0; d < np; ++d) {  // ascending k: the first k that attains the maximum wins (organism.c:365)
+        const int k = cj[(i - 1) * kCandCap + d];
+        if (k <= j) {
+          const double cand = (cv[(i - 1) * kCandCap + d] + G[j - k]) + rj;
+          if (best < cand) {
+            best = cand;
+            arg = d;
+          }
+        }
+      }
+      cv[i * kCandCap + lane] = best;
+      cr[i * kCandCap + lane] = rj;
+      ca[i * kCandCap + lane] = arg;
+    }
+    __syncwarp();
+  }
+  // (4) first maximum of the last row (_aux.c:149-158) and traceback (organism.c:398-427)
+  if (lane == 0) {
+    int c = 0;
+    const int cnt = cn[n - 1];
+    for (int d = 1; d < cnt; ++d)
+      if (cv[(n - 1) * kCandCap + d] > cv[(n - 1) * kCandCap + c]) c = d;
+    const size_t pair = (size_t)v.o * p.n_seq_total + seq;
+    p.E[pair] = cv[(n - 1) * kCandCap + c];
+    if (f.want_trace) {
+      for (int i = n - 1; i >= 1; --i) {
+        const int d = ca[i * kCandCap + c];
+        const int j = cj[i * kCandCap + c];
+        const int k = cj[(i - 1) * kCandCap + (d < 0 ? 0 : d)];
+        const int gap = d < 0 ? 0 : j - k;
+        p.rsc[pair * p.max_rec + i] = cr[i * kCandCap + c];
+        p.csc[pair * p.max_rec + i - 1] = d < 0 ? 0.0 : sm.G[(size_t)(i - 1) * p.g_stride + kGPad + gap];
+        p.gaps[pair * p.max_rec + i] = gap;
+        c = d < 0 ? 0 : d;
+      }
+      p.rsc[pair * p.max_rec] = cr[c];
+      p.gaps[pair * p.max_rec] = cj[c];
+    }
+  }
+  __syncwarp();
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The fast kernel.  CTA = one organism x a chunk of sequences; a warp holds 32/TEAM pairs at a time, each
+// placed by a team of TEAM lanes with J x J register tiles of DPX cells.
+// ------------------------------------------------------------------------------------------------
+template <int J, int TEAM>
+__global__ void __launch_bounds__(128) place_fast_kernel(const FastParams f) {
+  constexpr int NT = 32 / TEAM;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const PlaceParams &p = f.base;
+  const int oi = blockIdx.x / p.chunks;
+  const int chunk = blockIdx.x - oi * p.chunks;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int tl = lane % TEAM, team = lane / TEAM;
+  const FastSmem sm = carve_fast(f, smem_raw, nwarps, NT);
+  const OrgView v = organism_prologue(p, p.org_list[oi], sm.pool, sm.G, sm.rec);
+  __syncthreads();
+  if (warp == 0) build_fast_plan(f, v, sm, lane);
+  __syncthreads();
+  const FastPlan &plan = *sm.plan;
+  const int n = v.n, P = v.P;
+  const int slot = warp * NT + team;
+  int *rowsq = sm.rowsq + (size_t)slot * f.slotq_stride;
+  unsigned *w = sm.seqw + (size_t)slot * f.seqw_stride;
+  const int nwords = (p.S + 15) >> 4;
+
+  const int first = chunk * p.seqs_per_cta;
+  const int last = min(p.class_count, first + p.seqs_per_cta);
+  for (int sbase = first + warp * NT; sbase < last; sbase += nwarps * NT) {
+    // the warp's NT pairs of this round (idle teams replay the last valid sequence and write nothing)
+    const int si = min(sbase + team, last - 1);
+    const bool live = (sbase + team) < last;
+    const int seq = p.order[p.class_begin + si];
+    bool decline = !plan.ok || f.has_unk[seq];
+    // ---- phase 1: integer pass ---------------------------------------------------------------------
+    if (plan.ok) {
+      const unsigned *pw = p.packed + p.word_off[seq];
+      for (int t = tl; t < f.seqw_stride; t += TEAM) w[t] = (t < nwords) ? __ldg(pw + t) : 0u;
+      __syncwarp();
+      {
+        const int *tab = sm.kmer + plan.kmer_off[0];
+        const int ng = plan.ngroups[0];
+        for (int j = tl; j < P + J; j += TEAM) rowsq[j] = (j < P) ? score_q(tab, ng, w, j) : 0;
+      }
+      __syncwarp();
+      for (int i = 1; i < n; ++i) {
+        const int *prev = rowsq + (size_t)(i - 1) * f.rowq_stride;
+        int *cur = rowsq + (size_t)i * f.rowq_stride;
+        const int *Gq = sm.Gq + (size_t)(i - 1) * f.gq_stride + kGPad;
+        dp_stage<J, TEAM, OpI32>(prev, cur, Gq, P, tl, plan.sent);
+        __syncwarp();
+        const int *tab = sm.kmer + plan.kmer_off[i];
+        const int ng = plan.ngroups[i];
+        const int fwd = sm.rec[i].fwd;
+        for (int j = tl; j < P + J; j += TEAM) cur[j] = (j < P) ? cur[j] + score_q(tab, ng, w, fwd + j) : 0;
+        __syncwarp();
+      }
+    }
+    // ---- phase 2: exact refinement, one pair after the other, whole warp ---------------------------------
+    for (int t = 0; t < NT; ++t) {
+      const int t_seq = __shfl_sync(0xffffffffu, seq, t * TEAM);
+      const int t_live = __shfl_sync(0xffffffffu, (int)live, t * TEAM);
+      const int t_decline = __shfl_sync(0xffffffffu, (int)decline, t * TEAM);
+      if (!t_live) continue;
+      bool done = false;
+      if (!t_decline) {
+        const int t_slot = warp * NT + t;
+        done = refine_pair(f, v, sm, sm.rowsq + (size_t)t_slot * f.slotq_stride,
+                           sm.seqw + (size_t)t_slot * f.seqw_stride, t_seq, warp, lane);
+      }
+      if (!done && lane == 0) {
+        const int idx = atomicAdd(f.fb_count, 1);
+        if (idx < f.fb_cap) f.fb_pairs[idx] = make_int2(v.o, t_seq);
+      }
+    }
+    __syncwarp();
+  }
+}

@@ -27,9 +27,9 @@
 #define BIG_NEG (-1e10)
 #define BIG_POS (1e10)
 
-constexpr int kGPad = 16;          // -inf entries on both sides of every G table (>= largest tile size J)
+constexpr int kGPad = 32;          // -inf entries on both sides of every G table (>= largest tile size J)
 constexpr int kMaxSmem = 232448;   // 227 KB opt-in limit per CTA on sm_100
-constexpr int kMaxJ = 9;
+constexpr int kMaxJ = 21;
 
 #define ERR_NAN_NULL 1
 
@@ -169,12 +169,25 @@ __device__ __forceinline__ double gap_energy(const double *__restrict__ pdf, dou
 }
 
 // ------------------------------------------------------------------------------------------------
-// One DP stage for one pair, executed by one warp:  cur[j] = max_{k<=j} (prev[k] + G[j-k]),  j < P.
+// One DP stage for one pair, executed by a TEAM of lanes:  cur[j] = max_{k<=j} (prev[k] + G[j-k]),  j < P.
 // (R_i[j] is added afterwards by the caller; fl(max + r) == max fl(. + r) because x -> fl(x+r) is monotone.)
-// G points at gap 0 and is readable on [-kGPad, P-1+kGPad] with -inf outside [0, P).
-// prev must be readable up to ceil(P/J)*J - 1 (values beyond P-1 are never selected: their G is -inf).
+// Op selects the arithmetic: exact double (DADD + compare/select) or int32 fixed point (one DPX VIADDMNMX).
+// G points at gap 0 and is readable on [-kGPad, P-1+kGPad] with `lowest` outside [0, P).
+// prev must be readable up to ceil(P/J)*J - 1; for doubles the values beyond P-1 are never selected because
+// their G is -inf, for ints the caller keeps them at 0 so that 0 + lowest cannot wrap.
 // ------------------------------------------------------------------------------------------------
-template <int J>
+struct OpF64 {
+  typedef double T;
+  static __device__ __forceinline__ T cell(T acc, T p, T g) {
+    const T c = p + g;
+    return (acc < c) ? c : acc;
+  }
+};
+struct OpI32 {
+  typedef int T;
+  static __device__ __forceinline__ T cell(T acc, T p, T g) { return __viaddmax_s32(p, g, acc); }
+};
+
 struct TileState {
   int b;      // row block of the current job (rows b*J .. b*J+J-1)
   int kb;     // next k block
@@ -183,10 +196,12 @@ struct TileState {
   int next_b; // row block of the second job, or -1
 };
 
-template <int J>
-__device__ __forceinline__ void tile_step(double (&A)[J], double (&B)[J], double (&acc)[J], TileState<J> &st,
-                                          const double *__restrict__ prev, double *__restrict__ cur,
-                                          const double *__restrict__ G, int P) {
+template <int J, class Op>
+__device__ __forceinline__ void tile_step(typename Op::T (&A)[J], typename Op::T (&B)[J], typename Op::T (&acc)[J],
+                                          TileState &st, const typename Op::T *__restrict__ prev,
+                                          typename Op::T *__restrict__ cur, const typename Op::T *__restrict__ G, int P,
+                                          typename Op::T lowest) {
+  typedef typename Op::T T;
   if (st.kb == st.kend) {
     // job finished: flush its rows, then start the folded partner block (or idle)
     const int r0 = st.b * J;
@@ -203,17 +218,17 @@ __device__ __forceinline__ void tile_step(double (&A)[J], double (&B)[J], double
       st.kstep = 0;
     }
     st.kb = 0;
-    const double *ga = G + st.b * J + (J - 1);
+    const T *ga = G + st.b * J + (J - 1);
 #pragma unroll
     for (int t = 0; t < J; ++t) {
-      acc[t] = neg_inf();
+      acc[t] = lowest;
       A[t] = ga[-t];
     }
   }
   // A[i] = G[c - i], B[i] = G[c - J - i] with c = (b - kb)*J + J-1: row t at step u needs G[(b-kb)*J + t - u]
-  const double *gb = G + (st.b - st.kb) * J - 1;
-  const double *pk = prev + st.kb * J;
-  double pv[J];
+  const T *gb = G + (st.b - st.kb) * J - 1;
+  const T *pk = prev + st.kb * J;
+  T pv[J];
 #pragma unroll
   for (int u = 0; u < J; ++u) {
     B[u] = gb[-u];
@@ -223,24 +238,26 @@ __device__ __forceinline__ void tile_step(double (&A)[J], double (&B)[J], double
   for (int u = 0; u < J; ++u) {
 #pragma unroll
     for (int t = 0; t < J; ++t) {
-      const double g = (u <= t) ? A[J - 1 - t + u] : B[u - t - 1];
-      const double cand = pv[u] + g;
-      acc[t] = (acc[t] < cand) ? cand : acc[t];
+      const T g = (u <= t) ? A[J - 1 - t + u] : B[u - t - 1];
+      acc[t] = Op::cell(acc[t], pv[u], g);
     }
   }
   st.kb += st.kstep;
 }
 
-template <int J>
-__device__ __forceinline__ void dp_stage(const double *__restrict__ prev, double *__restrict__ cur,
-                                         const double *__restrict__ G, int P, int lane) {
+// `tl` = lane index inside the team (0..TEAM-1).  Rounds of 2*TEAM row blocks; inside a round lane tl owns block
+// tl and the mirrored block, so every lane of the team runs the same number of tiles.
+template <int J, int TEAM, class Op>
+__device__ __forceinline__ void dp_stage(const typename Op::T *__restrict__ prev, typename Op::T *__restrict__ cur,
+                                         const typename Op::T *__restrict__ G, int P, int tl, typename Op::T lowest) {
+  typedef typename Op::T T;
   const int NB = (P + J - 1) / J;
-  for (int r0 = 0; r0 < NB; r0 += 64) {
-    const int nbr = min(64, NB - r0);
+  for (int r0 = 0; r0 < NB; r0 += 2 * TEAM) {
+    const int nbr = min(2 * TEAM, NB - r0);
     const int half = (nbr + 1) >> 1;
-    const int bA = r0 + lane, bB = r0 + nbr - 1 - lane;
-    TileState<J> st;
-    if (lane < half) {
+    const int bA = r0 + tl, bB = r0 + nbr - 1 - tl;
+    TileState st;
+    if (tl < half) {
       st.b = bA;
       st.kend = bA + 1;
       st.kstep = 1;
@@ -252,19 +269,19 @@ __device__ __forceinline__ void dp_stage(const double *__restrict__ prev, double
       st.next_b = -1;
     }
     st.kb = 0;
-    double acc[J], A[J], B[J];
+    T acc[J], A[J], B[J];
     {
-      const double *ga = G + st.b * J + (J - 1);
+      const T *ga = G + st.b * J + (J - 1);
 #pragma unroll
       for (int t = 0; t < J; ++t) {
-        acc[t] = neg_inf();
+        acc[t] = lowest;
         A[t] = ga[-t];
       }
     }
     const int iters = 2 * r0 + nbr + 1;  // (bA+1) + (bB+1) for every folded lane
     for (int it = 0; it < iters; it += 2) {
-      tile_step<J>(A, B, acc, st, prev, cur, G, P);
-      tile_step<J>(B, A, acc, st, prev, cur, G, P);
+      tile_step<J, Op>(A, B, acc, st, prev, cur, G, P, lowest);
+      tile_step<J, Op>(B, A, acc, st, prev, cur, G, P, lowest);
     }
     if (st.kstep) {  // the last job of this lane has not been flushed by a later step
       const int rr = st.b * J;
@@ -276,148 +293,198 @@ __device__ __forceinline__ void dp_stage(const double *__restrict__ prev, double
 }
 
 // ------------------------------------------------------------------------------------------------
-// The fused kernel.  J = tile size (rows per lane block), chosen by the host from P (64*J >= P when possible).
+// Shared pieces of the placement kernels
+// ------------------------------------------------------------------------------------------------
+struct OrgView {
+  int o, n, sumL, P, eff;
+};
+
+// Organism prologue (all threads of the CTA): recognizer tables and descriptors into shared memory and the
+// exact gap-energy tables G[c][g] (connector.c:35-66 hoisted; -inf outside [0, P)).  Caller syncs afterwards.
+__device__ __forceinline__ OrgView organism_prologue(const PlaceParams &p, int o, double *s_pool, double *s_G, RecDesc *s_rec) {
+  OrgView v;
+  const int tid = threadIdx.x;
+  const int rb = p.rec_begin[o];
+  v.o = o;
+  v.n = p.rec_begin[o + 1] - rb;
+  v.sumL = p.sum_len[o];
+  v.P = p.S - v.sumL + 1;
+  v.eff = p.S - v.sumL + v.n;
+  const long long pb = p.pool_begin[o];
+  const int pn = (int)(p.pool_begin[o + 1] - pb);
+  for (int i = tid; i < pn; i += blockDim.x) s_pool[i] = __ldg(p.rec_pool + pb + i);
+  if (tid == 0) {
+    int fwd = 0;
+    for (int i = 0; i < v.n; ++i) {
+      RecDesc d;
+      const char t = p.rec_type[rb + i];
+      d.kind = (t == 'p' || t == 'P') ? 0 : (t == 'm' || t == 'M') ? 1 : (t == 't' || t == 'T') ? 2 : (t == 'r' || t == 'R') ? 3 : 4;
+      d.len = p.rec_len[rb + i];
+      d.nb = p.rec_nb[rb + i];
+      d.data = (int)(p.rec_data[rb + i] - pb);
+      d.fwd = fwd;
+      d.pad = 0;
+      fwd += d.len;
+      s_rec[i] = d;
+    }
+  }
+  const int M = p.con_M[o];
+  const double *D = p.tables + T_DEN;
+  for (int c = 0; c < v.n - 1; ++c) {
+    const double *pdf = p.con_pool + p.con_begin[o] + (long long)c * (2 * M + 2) + 2;
+    const double auc = __ldg(pdf + (M - 1) + (p.S - v.sumL));  // cdf pointer = pdf + max_len, max_len = M-1 (connector.c:3-4)
+    double *Gc = s_G + (size_t)c * p.g_stride;
+    for (int i = tid; i < p.g_stride; i += blockDim.x) {
+      const int g = i - kGPad;
+      Gc[i] = (g < 0 || g >= v.P) ? neg_inf() : gap_energy(pdf, auc, g, v.n, v.eff, D);
+    }
+  }
+  return v;
+}
+
+// 2-bit bases (+ unknown mask) of one sequence into byte codes (0..3, 4 = unknown), by one warp.
+__device__ __forceinline__ void unpack_codes(const PlaceParams &p, int seq, unsigned char *codes, int lane) {
+  const unsigned *pw = p.packed + p.word_off[seq];
+  const unsigned *uw = p.unk + p.unk_off[seq];
+  for (int b = lane; b < p.S; b += 32) {
+    const unsigned w = __ldg(pw + (b >> 4));
+    const unsigned u = __ldg(uw + (b >> 5));
+    const unsigned code = (w >> (2 * (b & 15))) & 3u;
+    codes[b] = ((u >> (b & 31)) & 1u) ? 4 : (unsigned char)code;
+  }
+}
+
+// One (organism, sequence) pair by one warp, exact fp64: score rows, chain DP, first maximum, optional traceback.
+template <int J, bool TRACE>
+__device__ __forceinline__ void place_pair_exact(const PlaceParams &p, const OrgView &v, int seq, const double *s_pool,
+                                                 const double *s_G, const RecDesc *s_rec, double *rows,
+                                                 unsigned char *codes, int lane, int &err) {
+  const int n = v.n, P = v.P;
+  unpack_codes(p, seq, codes, lane);
+  __syncwarp();
+
+  // ---- stage 0: C_0 = R_0 (organism.c:381-385) --------------------------------------------------
+  for (int j = lane; j < P; j += 32) rows[j] = score_rec(s_rec[0], s_pool, codes, j, p.tables, err);
+  __syncwarp();
+
+  // ---- stages 1..n-1: C_i[j] = max_k (C_{i-1}[k] + G[j-k]) + R_i[j] (organism.c:347-369) ----------
+  for (int i = 1; i < n; ++i) {
+    const double *prev = rows + (size_t)(TRACE ? (i - 1) : ((i - 1) & 1)) * p.row_stride;
+    double *cur = rows + (size_t)(TRACE ? i : (i & 1)) * p.row_stride;
+    const double *Gc = s_G + (size_t)(i - 1) * p.g_stride + kGPad;
+    dp_stage<J, 32, OpF64>(prev, cur, Gc, P, lane, neg_inf());
+    __syncwarp();
+    const RecDesc rd = s_rec[i];
+    const unsigned char *ci = codes + rd.fwd;
+    for (int j = lane; j < P; j += 32) cur[j] = cur[j] + score_rec(rd, s_pool, ci, j, p.tables, err);
+    __syncwarp();
+  }
+
+  // ---- first maximum of the last row (_aux.c:149-158) --------------------------------------------
+  const double *lastrow = rows + (size_t)(TRACE ? (n - 1) : ((n - 1) & 1)) * p.row_stride;
+  double bv = neg_inf();
+  int bi = 0x7fffffff;
+  for (int j = lane; j < P; j += 32) {
+    const double x = lastrow[j];
+    if (bi == 0x7fffffff || x > bv) { bv = x; bi = j; }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+    const int ob = __shfl_xor_sync(0xffffffffu, bi, off);
+    if (ob != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && ob < bi))) { bv = ov; bi = ob; }
+  }
+  const size_t pair = (size_t)v.o * p.n_seq_total + seq;
+  if (lane == 0) p.E[pair] = bv;
+
+  // ---- traceback (organism.c:398-427): re-scan one column per stage for the first k that reproduces
+  //      the stored value exactly -- identical to the reference's strict '<' update rule ---------------
+  if (TRACE) {
+    int m = bi;
+    for (int i = n - 1; i >= 1; --i) {
+      const double *prev = rows + (size_t)(i - 1) * p.row_stride;
+      const double *Gc = s_G + (size_t)(i - 1) * p.g_stride + kGPad;
+      const RecDesc rd = s_rec[i];
+      const double ri = score_rec(rd, s_pool, codes + rd.fwd, m, p.tables, err);
+      const double target = rows[(size_t)i * p.row_stride + m];
+      int found = -1;
+      for (int kb = 0; kb <= m && found < 0; kb += 32) {
+        const int k = kb + lane;
+        const bool hit = (k <= m) && ((prev[k] + Gc[m - k]) + ri == target);
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (bal) found = kb + __ffs(bal) - 1;
+      }
+      const int gap = found < 0 ? 0 : m - found;  // nothing ever won: the reference keeps its calloc'ed zeros
+      if (lane == 0) {
+        p.rsc[pair * p.max_rec + i] = ri;
+        p.csc[pair * p.max_rec + i - 1] = found < 0 ? 0.0 : Gc[gap];
+        p.gaps[pair * p.max_rec + i] = gap;
+      }
+      m -= gap;
+    }
+    if (lane == 0) {
+      p.rsc[pair * p.max_rec] = rows[m];
+      p.gaps[pair * p.max_rec] = m;
+    }
+  }
+  __syncwarp();
+}
+
+// Shared-memory carve-up of the exact kernels.
+struct ExactSmem {
+  double *pool, *G, *rows;
+  RecDesc *rec;
+  unsigned char *codes;
+};
+__device__ __forceinline__ ExactSmem carve_exact(const PlaceParams &p, unsigned char *raw, int nwarps) {
+  ExactSmem s;
+  s.pool = reinterpret_cast<double *>(raw);
+  s.G = s.pool + p.pool_stride;
+  s.rows = s.G + (size_t)(p.max_rec - 1) * p.g_stride;
+  s.rec = reinterpret_cast<RecDesc *>(s.rows + (size_t)nwarps * p.nrows * p.row_stride);
+  s.codes = reinterpret_cast<unsigned char *>(s.rec + p.max_rec);
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The exact fused kernel: CTA = one organism x a chunk of sequences; J = tile size chosen by the host from P.
 // ------------------------------------------------------------------------------------------------
 template <int J, bool TRACE>
 __global__ void __launch_bounds__(256) place_tiled_kernel(const PlaceParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int oi = blockIdx.x / p.chunks;
   const int chunk = blockIdx.x - oi * p.chunks;
-  const int o = p.org_list[oi];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const int rb = p.rec_begin[o];
-  const int n = p.rec_begin[o + 1] - rb;
-  const int S = p.S;
-  const int sumL = p.sum_len[o];
-  const int P = S - sumL + 1;
-  const int eff = S - sumL + n;
-
-  double *s_pool = reinterpret_cast<double *>(smem_raw);
-  double *s_G = s_pool + p.pool_stride;
-  double *s_rows = s_G + (size_t)(p.max_rec - 1) * p.g_stride;
-  RecDesc *s_rec = reinterpret_cast<RecDesc *>(s_rows + (size_t)nwarps * p.nrows * p.row_stride);
-  unsigned char *s_codes = reinterpret_cast<unsigned char *>(s_rec + p.max_rec);
-
-  // ---- organism prologue: tables into shared memory, gap-energy tables G[c][g] -------------------
-  {
-    const long long pb = p.pool_begin[o];
-    const int pn = (int)(p.pool_begin[o + 1] - pb);
-    for (int i = tid; i < pn; i += blockDim.x) s_pool[i] = __ldg(p.rec_pool + pb + i);
-    if (tid == 0) {
-      int fwd = 0;
-      for (int i = 0; i < n; ++i) {
-        RecDesc d;
-        const char t = p.rec_type[rb + i];
-        d.kind = (t == 'p' || t == 'P') ? 0 : (t == 'm' || t == 'M') ? 1 : (t == 't' || t == 'T') ? 2 : (t == 'r' || t == 'R') ? 3 : 4;
-        d.len = p.rec_len[rb + i];
-        d.nb = p.rec_nb[rb + i];
-        d.data = (int)(p.rec_data[rb + i] - pb);
-        d.fwd = fwd;
-        d.pad = 0;
-        fwd += d.len;
-        s_rec[i] = d;
-      }
-    }
-    const int M = p.con_M[o];
-    const double *D = p.tables + T_DEN;
-    for (int c = 0; c < n - 1; ++c) {
-      const double *pdf = p.con_pool + p.con_begin[o] + (long long)c * (2 * M + 2) + 2;
-      const double auc = __ldg(pdf + (M - 1) + (S - sumL));  // cdf pointer = pdf + max_len, max_len = M-1 (connector.c:3-4)
-      double *Gc = s_G + (size_t)c * p.g_stride;
-      for (int i = tid; i < p.g_stride; i += blockDim.x) {
-        const int g = i - kGPad;
-        Gc[i] = (g < 0 || g >= P) ? neg_inf() : gap_energy(pdf, auc, g, n, eff, D);
-      }
-    }
-  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const ExactSmem sm = carve_exact(p, smem_raw, nwarps);
+  const OrgView v = organism_prologue(p, p.org_list[oi], sm.pool, sm.G, sm.rec);
   __syncthreads();
-
-  double *rows = s_rows + (size_t)warp * p.nrows * p.row_stride;
-  unsigned char *codes = s_codes + (size_t)warp * p.code_stride;
+  double *rows = sm.rows + (size_t)warp * p.nrows * p.row_stride;
+  unsigned char *codes = sm.codes + (size_t)warp * p.code_stride;
   int err = 0;
-
   const int first = chunk * p.seqs_per_cta;
   const int last = min(p.class_count, first + p.seqs_per_cta);
-  for (int si = first + warp; si < last; si += nwarps) {
-    const int seq = p.order[p.class_begin + si];
-    // ---- unpack 2-bit bases (+ unknown mask) into byte codes ------------------------------------
-    {
-      const unsigned *pw = p.packed + p.word_off[seq];
-      const unsigned *uw = p.unk + p.unk_off[seq];
-      for (int b = lane; b < S; b += 32) {
-        const unsigned w = __ldg(pw + (b >> 4));
-        const unsigned u = __ldg(uw + (b >> 5));
-        const unsigned code = (w >> (2 * (b & 15))) & 3u;
-        codes[b] = ((u >> (b & 31)) & 1u) ? 4 : (unsigned char)code;
-      }
-    }
-    __syncwarp();
+  for (int si = first + warp; si < last; si += nwarps)
+    place_pair_exact<J, TRACE>(p, v, p.order[p.class_begin + si], sm.pool, sm.G, sm.rec, rows, codes, lane, err);
+  if (err) atomicOr(p.err_flag, err);
+}
 
-    // ---- stage 0: C_0 = R_0 (organism.c:381-385) ------------------------------------------------
-    for (int j = lane; j < P; j += 32) rows[j] = score_rec(s_rec[0], s_pool, codes, j, p.tables, err);
-    __syncwarp();
-
-    // ---- stages 1..n-1: C_i[j] = max_k (C_{i-1}[k] + G[j-k]) + R_i[j] (organism.c:347-369) --------
-    for (int i = 1; i < n; ++i) {
-      const double *prev = rows + (size_t)(TRACE ? (i - 1) : ((i - 1) & 1)) * p.row_stride;
-      double *cur = rows + (size_t)(TRACE ? i : (i & 1)) * p.row_stride;
-      const double *Gc = s_G + (size_t)(i - 1) * p.g_stride + kGPad;
-      dp_stage<J>(prev, cur, Gc, P, lane);
-      __syncwarp();
-      const RecDesc rd = s_rec[i];
-      const unsigned char *ci = codes + rd.fwd;
-      for (int j = lane; j < P; j += 32) cur[j] = cur[j] + score_rec(rd, s_pool, ci, j, p.tables, err);
-      __syncwarp();
-    }
-
-    // ---- first maximum of the last row (_aux.c:149-158) ------------------------------------------
-    const double *lastrow = rows + (size_t)(TRACE ? (n - 1) : ((n - 1) & 1)) * p.row_stride;
-    double bv = neg_inf();
-    int bi = 0x7fffffff;
-    for (int j = lane; j < P; j += 32) {
-      const double v = lastrow[j];
-      if (bi == 0x7fffffff || v > bv) { bv = v; bi = j; }
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
-      const int ob = __shfl_xor_sync(0xffffffffu, bi, off);
-      if (ob != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && ob < bi))) { bv = ov; bi = ob; }
-    }
-    const size_t pair = (size_t)o * p.n_seq_total + seq;
-    if (lane == 0) p.E[pair] = bv;
-
-    // ---- traceback (organism.c:398-427): re-scan one column per stage for the first k that reproduces
-    //      the stored value exactly -- identical to the reference's strict '<' update rule -------------
-    if (TRACE) {
-      int m = bi;
-      for (int i = n - 1; i >= 1; --i) {
-        const double *prev = rows + (size_t)(i - 1) * p.row_stride;
-        const double *Gc = s_G + (size_t)(i - 1) * p.g_stride + kGPad;
-        const RecDesc rd = s_rec[i];
-        const double ri = score_rec(rd, s_pool, codes + rd.fwd, m, p.tables, err);
-        const double target = rows[(size_t)i * p.row_stride + m];
-        int found = -1;
-        for (int kb = 0; kb <= m && found < 0; kb += 32) {
-          const int k = kb + lane;
-          const bool hit = (k <= m) && ((prev[k] + Gc[m - k]) + ri == target);
-          const unsigned bal = __ballot_sync(0xffffffffu, hit);
-          if (bal) found = kb + __ffs(bal) - 1;
-        }
-        const int gap = found < 0 ? 0 : m - found;  // nothing ever won: the reference keeps its calloc'ed zeros
-        if (lane == 0) {
-          p.rsc[pair * p.max_rec + i] = ri;
-          p.csc[pair * p.max_rec + i - 1] = found < 0 ? 0.0 : Gc[gap];
-          p.gaps[pair * p.max_rec + i] = gap;
-        }
-        m -= gap;
-      }
-      if (lane == 0) {
-        p.rsc[pair * p.max_rec] = rows[m];
-        p.gaps[pair * p.max_rec] = m;
-      }
-    }
-    __syncwarp();
+// ------------------------------------------------------------------------------------------------
+// List mode: the pairs the integer fast path declined (too many near-ties, unknown bytes, tables that do
+// not fit its fixed-point range).  One warp per CTA, grid-stride over the device-side list.
+// ------------------------------------------------------------------------------------------------
+template <bool TRACE>
+__global__ void __launch_bounds__(32) place_list_kernel(const PlaceParams p, const int *__restrict__ fb_count,
+                                                        const int2 *__restrict__ fb_pairs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const ExactSmem sm = carve_exact(p, smem_raw, 1);
+  const int count = *fb_count;
+  int err = 0;
+  for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
+    const int2 pr = fb_pairs[idx];
+    __syncthreads();
+    const OrgView v = organism_prologue(p, pr.x, sm.pool, sm.G, sm.rec);
+    __syncthreads();
+    place_pair_exact<5, TRACE>(p, v, pr.y, sm.pool, sm.G, sm.rec, sm.rows, sm.codes, threadIdx.x, err);
   }
   if (err) atomicOr(p.err_flag, err);
 }

@@ -54,6 +54,8 @@ class Engine:
         self._ctx = handle
         self._packed: PackedPopulation | None = None
         self._sets: dict[int, SequenceSet] = {}
+        # True: skip the integer filter pass and place every pair with the exact fp64 kernel (same results)
+        self.exact_only = os.environ.get("FLEMINGO_EXACT_ONLY", "0") == "1"
 
     # -- lifetime -------------------------------------------------------------------------------
     def close(self):
@@ -142,7 +144,7 @@ class Engine:
                 gaps = np.empty((n_org, n_seq, mr), dtype=np.int32)
                 rsc = np.empty((n_org, n_seq, mr), dtype=np.float64)
                 csc = np.empty((n_org, n_seq, mr), dtype=np.float64)
-        flags = _cabi.FL_WANT_TRACE if trace else 0
+        flags = (_cabi.FL_WANT_TRACE if trace else 0) | (_cabi.FL_EXACT_ONLY if self.exact_only else 0)
         _cabi.check(self._lib.fl_place_batch(self._ctx, sset.set_id, _ptr(con_begin), flags, _ptr(energies), _ptr(gaps),
                                              _ptr(rsc), _ptr(csc)))
         if not fetch:

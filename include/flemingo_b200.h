@@ -39,6 +39,7 @@ extern "C" {
 
 /* flags of fl_place_batch */
 #define FL_WANT_TRACE 1   /* also produce start/gaps and per-node scores (organism.c:398-427) */
+#define FL_EXACT_ONLY 2   /* skip the integer filter pass: every pair goes through the exact fp64 kernel */
 
 /* fitness methods, src/objects/organism_object.py:848-936 */
 #define FL_FIT_WELCH 0

@@ -39,10 +39,15 @@ def golden_cases(golden, golden_null_models):
     return [(case, build_case_organism(case)) for case in golden["cases"]]
 
 
-@pytest.fixture(scope="session")
-def engine():
+@pytest.fixture(scope="session", params=["filter+refine", "exact-only"])
+def engine(request):
+    """The process-wide engine, once with the integer filter pass enabled and once with every pair forced
+    through the exact fp64 kernel -- both must reproduce the reference bit for bit."""
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from flemingo_b200.engine import get_engine
-    return get_engine()
+    eng = get_engine()
+    eng.exact_only = request.param == "exact-only"
+    yield eng
+    eng.exact_only = False

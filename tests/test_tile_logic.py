@@ -9,8 +9,8 @@ REPO = Path(__file__).resolve().parents[1]
 
 def test_tiled_dp_stage_equals_naive(tmp_path):
     src = (REPO / "flemingo_b200" / "csrc" / "place_kernel.cuh").read_text()
-    start = src.index("template <int J>\nstruct TileState")
-    end = src.index("// ------------------------------------------------------------------------------------------------\n// The fused kernel")
+    start = src.index("struct OpF64 {")
+    end = src.index("// ------------------------------------------------------------------------------------------------\n// Shared pieces of the placement kernels")
     (tmp_path / "tile_extract.h").write_text(src[start:end])
     exe = tmp_path / "test_tile"
     subprocess.run(["g++", "-O2", "-std=c++17", f'-DTILE_EXTRACT="{tmp_path / "tile_extract.h"}"', "-o", str(exe),
