@@ -154,7 +154,7 @@ struct Population {
 struct fl_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  DevBuf tables, err_flag, con_begin, org_list, gaps, rsc, csc, fit_out, fit_scratch, fb_count, fb_pairs;
+  DevBuf tables, err_flag, con_begin, org_list, gaps, rsc, csc, fit_out, fit_scratch, fb_count, fb_pairs, fast_scratch;
   long long fast_pairs = 0, fallback_pairs = 0;  // statistics of the last fl_place_batch
   Population pop, scratch_pop;
   SeqSet sets[FL_MAX_SETS + 1];  // the extra slot serves fl_calculate
@@ -215,7 +215,7 @@ extern "C" int fl_ctx_destroy(fl_ctx *ctx) {
   }
   release_pop(ctx->pop);
   release_pop(ctx->scratch_pop);
-  DevBuf *bufs[] = {&ctx->tables, &ctx->err_flag, &ctx->con_begin, &ctx->org_list, &ctx->gaps, &ctx->rsc, &ctx->csc, &ctx->fit_out, &ctx->fit_scratch, &ctx->fb_count, &ctx->fb_pairs};
+  DevBuf *bufs[] = {&ctx->tables, &ctx->err_flag, &ctx->con_begin, &ctx->org_list, &ctx->gaps, &ctx->rsc, &ctx->csc, &ctx->fit_out, &ctx->fit_scratch, &ctx->fb_count, &ctx->fb_pairs, &ctx->fast_scratch};
   for (DevBuf *b : bufs) b->release();
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -521,7 +521,6 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
     const bool allow_fast = !(flags & FL_EXACT_ONLY);
     FastParams fp;
     fp.gq_stride = kGPad + Pmax + kGPad;
-    fp.rowq_stride = (Pmax + kMaxJ + 4) & ~3;
     fp.seqw_stride = (cl.len + 15) / 16 + 3;
     fp.bitmap_words = (Pmax + 31) / 32 + 1;
     fp.want_trace = trace ? 1 : 0;
@@ -540,24 +539,32 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
       }
     }
     fp.kmer_cap = kmer_cap;
-    // fast-path geometry; if even one warp per CTA does not fit, those organisms go to the exact kernel
-    int fast_warps[kNumFastConfigs];
+    // fast-path geometry: warps per CTA chosen for the most resident warps per SM; if even one warp does not fit,
+    // those organisms go to the exact kernel
+    int fast_warps[kNumFastConfigs], fast_rowq[kNumFastConfigs], fast_slot[kNumFastConfigs], fast_ctas_per_sm[kNumFastConfigs];
     size_t fast_smem[kNumFastConfigs];
     for (int j = 0; j < kNumFastConfigs; ++j) {
       fast_warps[j] = 0;
       fast_smem[j] = 0;
       if (fast_bucket[j].empty()) continue;
       const int team = kFastConfigs[j].team, nt = 32 / team;
-      const int slot = (((P.max_rec * fp.rowq_stride) + 31) & ~31) + (team & 31);
-      for (int nw = 4; nw >= 1; nw >>= 1) {
-        const size_t d = (size_t)pp.pool_stride + (size_t)(P.max_rec - 1) * pp.g_stride + 2ull * nw * P.max_rec * kCandCap;
-        const size_t i = (size_t)(P.max_rec - 1) * fp.gq_stride + fp.kmer_cap + (size_t)nw * nt * slot + (size_t)nw * nt * fp.seqw_stride +
+      fast_rowq[j] = (Pmax + kFastConfigs[j].J + 3) & ~3;
+      fast_slot[j] = ((2 * fast_rowq[j] + 31) & ~31) + (team & 31);
+      int best_occ = 0;
+      static const int kWarpChoices[] = {16, 12, 10, 8, 6, 4, 2, 1};
+      for (int nw : kWarpChoices) {
+        const size_t d = (size_t)pp.pool_stride + 2ull * nw * P.max_rec * kCandCap;
+        const size_t i = (size_t)(P.max_rec - 1) * fp.gq_stride + fp.kmer_cap + (size_t)nw * nt * fast_slot[j] + (size_t)nw * nt * fp.seqw_stride +
                          2ull * nw * P.max_rec * kCandCap + (size_t)nw * P.max_rec + (size_t)nw * fp.bitmap_words;
         const size_t bytes = d * 8 + i * 4 + sizeof(RecDesc) * P.max_rec + sizeof(FastPlan) + 16;
-        if (bytes <= (size_t)kMaxSmem) {
+        if (bytes > (size_t)kMaxSmem) continue;
+        const int ctas = (int)std::min<size_t>(233472 / (bytes + 1024), 32);
+        const int occ = std::min(ctas * nw, 20);  // ~96 registers per thread cap residency at ~20 warps
+        if (occ > best_occ) {
+          best_occ = occ;
           fast_warps[j] = nw;
           fast_smem[j] = bytes;
-          break;
+          fast_ctas_per_sm[j] = std::max(1, std::min(ctas, 20 / nw));
         }
       }
       if (!fast_warps[j]) {
@@ -608,11 +615,14 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
         const int n_b = (int)fast_bucket[j].size();
         if (!n_b) continue;
         const int team = kFastConfigs[j].team, nt = 32 / team, nw = fast_warps[j];
-        fp.slotq_stride = (((P.max_rec * fp.rowq_stride) + 31) & ~31) + (team & 31);
+        fp.rowq_stride = fast_rowq[j];
+        fp.slotq_stride = fast_slot[j];
+        fp.scratch_slot_stride = (long long)P.max_rec * fast_rowq[j];
         const int per_round = nw * nt;
         const long long pairs = (long long)n_b * cl.count;
-        int spc = (int)std::max<long long>(per_round, (pairs + target_ctas - 1) / target_ctas);
-        spc = std::min(spc, std::max(per_round, 128));
+        const long long fast_target = (long long)n_sm * fast_ctas_per_sm[j] * 6;
+        int spc = (int)std::max<long long>(per_round, (pairs + fast_target - 1) / fast_target);
+        spc = std::min(spc, std::max(per_round, 256));
         spc = ((spc + per_round - 1) / per_round) * per_round;
         fp.base = pp;
         fp.base.org_list = d_list + fast_begin[j];
@@ -620,6 +630,8 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
         fp.base.chunks = (cl.count + spc - 1) / spc;
         const long long grid = (long long)n_b * fp.base.chunks;
         if (grid > 0x7fffffffLL) return fail(FL_E_UNSUPPORTED, "grid too large");
+        if ((rc = ctx->fast_scratch.ensure((size_t)grid * per_round * (size_t)fp.scratch_slot_stride * 4))) return rc;
+        fp.scratch = ctx->fast_scratch.as<int>();
         kFastConfigs[j].fn<<<(unsigned)grid, nw * 32, fast_smem[j], ctx->stream>>>(fp);
         CK(cudaGetLastError());
         ctx->launches++;

@@ -32,11 +32,13 @@ struct FastParams {
   int fb_cap;
   int gq_stride;     // ints per quantised connector table (kGPad + Pmax + kGPad)
   int rowq_stride;   // ints per quantised row
-  int slotq_stride;  // ints per pair slot (max_rec rows), == TEAM (mod 32) so that teams hit disjoint banks
+  int slotq_stride;  // ints per pair slot (2 ping-pong rows), == TEAM (mod 32) so that teams hit disjoint banks
   int seqw_stride;   // u32 words per packed sequence copy
   int kmer_cap;      // ints available for the 4-mer tables of one organism
   int bitmap_words;  // u32 words of the per-warp candidate bitmap
   int want_trace;
+  int *scratch;      // global rows 0..n-3 of every resident pair slot (only the last two rows stay in shared memory)
+  long long scratch_slot_stride;  // ints per pair slot in `scratch` (max_rec * rowq_stride)
 };
 
 struct FastPlan {
@@ -50,28 +52,18 @@ struct FastPlan {
 };
 
 struct FastSmem {
-  double *pool, *G, *cv, *cr;
+  double *pool, *cv, *cr;
   int *Gq, *kmer, *rowsq, *cj, *ca, *cn;
   unsigned *seqw, *bitmap;
   RecDesc *rec;
   FastPlan *plan;
 };
 
-__device__ __forceinline__ size_t fast_smem_bytes_dev(const FastParams &f, int nwarps, int nt) {
-  const PlaceParams &p = f.base;
-  size_t d = (size_t)p.pool_stride + (size_t)(p.max_rec - 1) * p.g_stride + 2ull * nwarps * p.max_rec * kCandCap;
-  size_t i = (size_t)(p.max_rec - 1) * f.gq_stride + f.kmer_cap + (size_t)nwarps * nt * f.slotq_stride +
-             (size_t)nwarps * nt * f.seqw_stride + 2ull * nwarps * p.max_rec * kCandCap + (size_t)nwarps * p.max_rec +
-             (size_t)nwarps * f.bitmap_words;
-  return d * 8 + i * 4 + sizeof(RecDesc) * p.max_rec + sizeof(FastPlan);
-}
-
 __device__ __forceinline__ FastSmem carve_fast(const FastParams &f, unsigned char *raw, int nwarps, int nt) {
   const PlaceParams &p = f.base;
   FastSmem s;
   s.pool = reinterpret_cast<double *>(raw);
-  s.G = s.pool + p.pool_stride;
-  s.cv = s.G + (size_t)(p.max_rec - 1) * p.g_stride;
+  s.cv = s.pool + p.pool_stride;
   s.cr = s.cv + (size_t)nwarps * p.max_rec * kCandCap;
   s.plan = reinterpret_cast<FastPlan *>(s.cr + (size_t)nwarps * p.max_rec * kCandCap);
   s.rec = reinterpret_cast<RecDesc *>(s.plan + 1);
@@ -160,12 +152,13 @@ __device__ void build_fast_plan(const FastParams &f, const OrgView &v, const Fas
     kmer_need += 256 * ((rd.len + 3) >> 2);
   }
   for (int c = 0; c < n - 1; ++c) {
-    const double *Gc = sm.G + (size_t)c * p.g_stride + kGPad;
+    const ConView cvw = connector_view(p, v, c);
     double lo = inf, hi = -inf;
     for (int g = lane; g <= P - 2; g += 32) {  // legit gaps; g = P-1 is the reference's -1e10 sentinel
-      lo = fmin(lo, Gc[g]);
-      hi = fmax(hi, Gc[g]);
-      bad |= (Gc[g] != Gc[g]);
+      const double x = exact_gap(p, v, cvw, g);
+      lo = fmin(lo, x);
+      hi = fmax(hi, x);
+      bad |= (x != x);
     }
     lo = warp_min(lo);
     hi = warp_max(hi);
@@ -221,10 +214,12 @@ __device__ void build_fast_plan(const FastParams &f, const OrgView &v, const Fas
     }
     lo_q_rec = lo_q;
     for (int c = 0; c < n - 1; ++c) {
-      const double *Gc = sm.G + (size_t)c * p.g_stride + kGPad;
+      const ConView cvw = connector_view(p, v, c);
+      int *Gq = sm.Gq + (size_t)c * f.gq_stride + kGPad;
       int lo = 0x7fffffff, hi = -0x7fffffff;
       for (int g = lane; g <= P - 2; g += 32) {
-        const int q = __double2int_rn(Gc[g] * s);
+        const int q = __double2int_rn(exact_gap(p, v, cvw, g) * s);
+        Gq[g] = q;
         lo = min(lo, q);
         hi = max(hi, q);
       }
@@ -242,11 +237,10 @@ __device__ void build_fast_plan(const FastParams &f, const OrgView &v, const Fas
   if (ok && (lo_q_rec + (long long)(n - 1) * sent < -2000000000LL || hi_q > 2000000000LL || lo_q < -2000000000LL)) ok = 0;
   if (ok) {
     for (int c = 0; c < n - 1; ++c) {
-      const double *Gc = sm.G + (size_t)c * p.g_stride + kGPad;
       int *Gq = sm.Gq + (size_t)c * f.gq_stride;
       for (int i = lane; i < f.gq_stride; i += 32) {
         const int g = i - kGPad;
-        Gq[i] = (g >= 0 && g <= P - 2) ? __double2int_rn(Gc[g] * s) : (int)sent;
+        if (!(g >= 0 && g <= P - 2)) Gq[i] = (int)sent;
       }
     }
   }
@@ -268,8 +262,13 @@ __device__ void build_fast_plan(const FastParams &f, const OrgView &v, const Fas
 // ---- exact refinement of one pair on its candidate sets (whole warp) -----------------------------------
 // rowsq: the pair's quantised rows [n][rowq_stride]; w: its packed sequence.  Returns false if a candidate set
 // overflowed (pair goes to the exact kernel).
-__device__ bool refine_pair(const FastParams &f, const OrgView &v, const FastSmem &sm, const int *rowsq, const unsigned *w,
-                            int seq, int warp, int lane) {
+// Quantised row i of a pair: the last two stages are still in the shared ping-pong buffers, older ones in global scratch.
+__device__ __forceinline__ const int *row_q(const FastParams &f, int n, int i, const int *rows_smem, const int *rows_glob) {
+  return (i >= n - 2) ? rows_smem + (size_t)(i & 1) * f.rowq_stride : rows_glob + (size_t)i * f.rowq_stride;
+}
+
+__device__ bool refine_pair(const FastParams &f, const OrgView &v, const FastSmem &sm, const int *rowsq, const int *rowsg,
+                            const unsigned *w, int seq, int warp, int lane) {
   const PlaceParams &p = f.base;
   const FastPlan &plan = *sm.plan;
   const int n = v.n, P = v.P;
@@ -283,7 +282,7 @@ __device__ bool refine_pair(const FastParams &f, const OrgView &v, const FastSme
 
   // (1) candidates on the last row
   {
-    const int *row = rowsq + (size_t)(n - 1) * f.rowq_stride;
+    const int *row = row_q(f, n, n - 1, rowsq, rowsg);
     int mx = -0x7fffffff;
     for (int j = lane; j < P; j += 32) mx = max(mx, row[j]);
     mx = warp_max_i(mx);
@@ -308,8 +307,8 @@ __device__ bool refine_pair(const FastParams &f, const OrgView &v, const FastSme
   for (int i = n - 1; i >= 1; --i) {
     for (int t = lane; t < words; t += 32) bitmap[t] = 0u;
     __syncwarp();
-    const int *prev = rowsq + (size_t)(i - 1) * f.rowq_stride;
-    const int *cur = rowsq + (size_t)i * f.rowq_stride;
+    const int *prev = row_q(f, n, i - 1, rowsq, rowsg);
+    const int *cur = row_q(f, n, i, rowsq, rowsg);
     const int *Gq = sm.Gq + (size_t)(i - 1) * f.gq_stride + kGPad;
     const int *tab = sm.kmer + plan.kmer_off[i];
     const int fwd = sm.rec[i].fwd;
@@ -351,14 +350,14 @@ __device__ bool refine_pair(const FastParams &f, const OrgView &v, const FastSme
       const int j = cj[i * kCandCap + lane];
       const RecDesc rd = sm.rec[i];
       const double rj = score_exact_packed(rd, sm.pool, w, rd.fwd + j);
-      const double *G = sm.G + (size_t)(i - 1) * p.g_stride + kGPad;
+      const ConView cvw = connector_view(p, v, i - 1);
       double best = neg_inf();
       int arg = -1;
       const int np = cn[i - 1];
       for (int d = 0; d < np; ++d) {  // ascending k: the first k that attains the maximum wins (organism.c:365)
         const int k = cj[(i - 1) * kCandCap + d];
         if (k <= j) {
-          const double cand = (cv[(i - 1) * kCandCap + d] + G[j - k]) + rj;
+          const double cand = (cv[(i - 1) * kCandCap + d] + exact_gap(p, v, cvw, j - k)) + rj;
           if (best < cand) {
             best = cand;
             arg = d;
@@ -386,7 +385,7 @@ __device__ bool refine_pair(const FastParams &f, const OrgView &v, const FastSme
         const int k = cj[(i - 1) * kCandCap + (d < 0 ? 0 : d)];
         const int gap = d < 0 ? 0 : j - k;
         p.rsc[pair * p.max_rec + i] = cr[i * kCandCap + c];
-        p.csc[pair * p.max_rec + i - 1] = d < 0 ? 0.0 : sm.G[(size_t)(i - 1) * p.g_stride + kGPad + gap];
+        p.csc[pair * p.max_rec + i - 1] = d < 0 ? 0.0 : exact_gap(p, v, connector_view(p, v, i - 1), gap);
         p.gaps[pair * p.max_rec + i] = gap;
         c = d < 0 ? 0 : d;
       }
@@ -403,7 +402,7 @@ __device__ bool refine_pair(const FastParams &f, const OrgView &v, const FastSme
 // placed by a team of TEAM lanes with J x J register tiles of DPX cells.
 // ------------------------------------------------------------------------------------------------
 template <int J, int TEAM>
-__global__ void __launch_bounds__(128) place_fast_kernel(const FastParams f) {
+__global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
   constexpr int NT = 32 / TEAM;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const PlaceParams &p = f.base;
@@ -412,7 +411,7 @@ __global__ void __launch_bounds__(128) place_fast_kernel(const FastParams f) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int tl = lane % TEAM, team = lane / TEAM;
   const FastSmem sm = carve_fast(f, smem_raw, nwarps, NT);
-  const OrgView v = organism_prologue(p, p.org_list[oi], sm.pool, sm.G, sm.rec);
+  const OrgView v = organism_prologue(p, p.org_list[oi], sm.pool, nullptr, sm.rec);
   __syncthreads();
   if (warp == 0) build_fast_plan(f, v, sm, lane);
   __syncthreads();
@@ -420,6 +419,7 @@ __global__ void __launch_bounds__(128) place_fast_kernel(const FastParams f) {
   const int n = v.n, P = v.P;
   const int slot = warp * NT + team;
   int *rowsq = sm.rowsq + (size_t)slot * f.slotq_stride;
+  int *rowsg = f.scratch + ((size_t)blockIdx.x * nwarps * NT + slot) * f.scratch_slot_stride;
   unsigned *w = sm.seqw + (size_t)slot * f.seqw_stride;
   const int nwords = (p.S + 15) >> 4;
 
@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(128) place_fast_kernel(const FastParams f) {
     const int si = min(sbase + team, last - 1);
     const bool live = (sbase + team) < last;
     const int seq = p.order[p.class_begin + si];
-    bool decline = !plan.ok || f.has_unk[seq];
+    const bool decline = !plan.ok || f.has_unk[seq];
     // ---- phase 1: integer pass ---------------------------------------------------------------------
     if (plan.ok) {
       const unsigned *pw = p.packed + p.word_off[seq];
@@ -439,19 +439,30 @@ __global__ void __launch_bounds__(128) place_fast_kernel(const FastParams f) {
       {
         const int *tab = sm.kmer + plan.kmer_off[0];
         const int ng = plan.ngroups[0];
-        for (int j = tl; j < P + J; j += TEAM) rowsq[j] = (j < P) ? score_q(tab, ng, w, j) : 0;
+        const bool spill = 0 <= n - 3;
+        for (int j = tl; j < P + J; j += TEAM) {
+          const int x = (j < P) ? score_q(tab, ng, w, j) : 0;
+          rowsq[j] = x;
+          if (spill && j < P) rowsg[j] = x;
+        }
       }
       __syncwarp();
       for (int i = 1; i < n; ++i) {
-        const int *prev = rowsq + (size_t)(i - 1) * f.rowq_stride;
-        int *cur = rowsq + (size_t)i * f.rowq_stride;
+        const int *prev = rowsq + (size_t)((i - 1) & 1) * f.rowq_stride;
+        int *cur = rowsq + (size_t)(i & 1) * f.rowq_stride;
         const int *Gq = sm.Gq + (size_t)(i - 1) * f.gq_stride + kGPad;
         dp_stage<J, TEAM, OpI32>(prev, cur, Gq, P, tl, plan.sent);
         __syncwarp();
         const int *tab = sm.kmer + plan.kmer_off[i];
         const int ng = plan.ngroups[i];
         const int fwd = sm.rec[i].fwd;
-        for (int j = tl; j < P + J; j += TEAM) cur[j] = (j < P) ? cur[j] + score_q(tab, ng, w, fwd + j) : 0;
+        const bool spill = i <= n - 3;
+        int *gl = rowsg + (size_t)i * f.rowq_stride;
+        for (int j = tl; j < P + J; j += TEAM) {
+          const int x = (j < P) ? cur[j] + score_q(tab, ng, w, fwd + j) : 0;
+          cur[j] = x;
+          if (spill && j < P) gl[j] = x;
+        }
         __syncwarp();
       }
     }
@@ -465,6 +476,7 @@ __global__ void __launch_bounds__(128) place_fast_kernel(const FastParams f) {
       if (!t_decline) {
         const int t_slot = warp * NT + t;
         done = refine_pair(f, v, sm, sm.rowsq + (size_t)t_slot * f.slotq_stride,
+                           f.scratch + ((size_t)blockIdx.x * nwarps * NT + t_slot) * f.scratch_slot_stride,
                            sm.seqw + (size_t)t_slot * f.seqw_stride, t_seq, warp, lane);
       }
       if (!done && lane == 0) {

@@ -301,6 +301,22 @@ struct OrgView {
 
 // Organism prologue (all threads of the CTA): recognizer tables and descriptors into shared memory and the
 // exact gap-energy tables G[c][g] (connector.c:35-66 hoisted; -inf outside [0, P)).  Caller syncs afterwards.
+struct ConView {
+  const double *pdf;  // pdf block of the connector (gap 0 first)
+  double auc;         // cdf[S - sumL] through the reference's shifted cdf pointer
+};
+__device__ __forceinline__ ConView connector_view(const PlaceParams &p, const OrgView &v, int c) {
+  const int M = p.con_M[v.o];
+  ConView cv;
+  cv.pdf = p.con_pool + p.con_begin[v.o] + (long long)c * (2 * M + 2) + 2;
+  cv.auc = __ldg(cv.pdf + (M - 1) + (p.S - v.sumL));  // cdf pointer = pdf + max_len, max_len = M-1 (connector.c:3-4)
+  return cv;
+}
+// exact gap energy of connector view cv for gap g (what the G tables hold)
+__device__ __forceinline__ double exact_gap(const PlaceParams &p, const OrgView &v, const ConView &cv, int g) {
+  return gap_energy(cv.pdf, cv.auc, g, v.n, v.eff, p.tables + T_DEN);
+}
+
 __device__ __forceinline__ OrgView organism_prologue(const PlaceParams &p, int o, double *s_pool, double *s_G, RecDesc *s_rec) {
   OrgView v;
   const int tid = threadIdx.x;
@@ -328,15 +344,14 @@ __device__ __forceinline__ OrgView organism_prologue(const PlaceParams &p, int o
       s_rec[i] = d;
     }
   }
-  const int M = p.con_M[o];
-  const double *D = p.tables + T_DEN;
-  for (int c = 0; c < v.n - 1; ++c) {
-    const double *pdf = p.con_pool + p.con_begin[o] + (long long)c * (2 * M + 2) + 2;
-    const double auc = __ldg(pdf + (M - 1) + (p.S - v.sumL));  // cdf pointer = pdf + max_len, max_len = M-1 (connector.c:3-4)
-    double *Gc = s_G + (size_t)c * p.g_stride;
-    for (int i = tid; i < p.g_stride; i += blockDim.x) {
-      const int g = i - kGPad;
-      Gc[i] = (g < 0 || g >= v.P) ? neg_inf() : gap_energy(pdf, auc, g, v.n, v.eff, D);
+  if (s_G != nullptr) {
+    for (int c = 0; c < v.n - 1; ++c) {
+      const ConView cv = connector_view(p, v, c);
+      double *Gc = s_G + (size_t)c * p.g_stride;
+      for (int i = tid; i < p.g_stride; i += blockDim.x) {
+        const int g = i - kGPad;
+        Gc[i] = (g < 0 || g >= v.P) ? neg_inf() : exact_gap(p, v, cv, g);
+      }
     }
   }
   return v;
