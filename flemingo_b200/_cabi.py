@@ -21,7 +21,7 @@ FIT_METHODS = {"Welch": 0, "Yuen": 1, "Trim-left-M": 2, "Trim-left-M-SD": 3}
 EXPORTED = [
     "fl_last_error", "fl_abi_version", "fl_ctx_create", "fl_ctx_destroy", "fl_ctx_stream", "fl_sync",
     "fl_upload_sequences", "fl_sequence_classes", "fl_upload_population", "fl_update_connectors", "fl_place_batch", "fl_fitness",
-    "fl_calculate", "fl_launch_count",
+    "fl_calculate", "fl_launch_count", "fl_path_stats",
 ]
 
 
@@ -31,6 +31,8 @@ class FlPopulation(C.Structure):
         ("rec_begin", C.c_void_p), ("rec_type", C.c_void_p), ("rec_len", C.c_void_p), ("rec_nb", C.c_void_p),
         ("rec_data", C.c_void_p), ("pool_begin", C.c_void_p), ("rec_pool", C.c_void_p), ("n_pool", C.c_longlong),
         ("con_M", C.c_void_p), ("con_pool", C.c_void_p), ("n_con", C.c_longlong),
+        ("rec_class", C.c_void_p), ("n_classes", C.c_int), ("cls_kind", C.c_void_p), ("cls_len", C.c_void_p),
+        ("cls_nb", C.c_void_p), ("cls_edges", C.c_void_p), ("edges_pool", C.c_void_p), ("n_edges", C.c_longlong),
     ]
 
 
@@ -70,6 +72,7 @@ def load_library() -> C.CDLL:
     lib.fl_place_batch.argtypes = [vp, ip, vp, ip, vp, vp, vp, vp]
     lib.fl_fitness.argtypes = [vp, ip, ip, ip, dp, vp]
     lib.fl_calculate.argtypes = [vp, vp, ip, vp, ip, vp, vp, vp, ll, vp, vp, vp, ip, vp, vp, vp]
+    lib.fl_path_stats.argtypes = [vp, C.POINTER(ll), C.POINTER(ll)]
     lib.fl_launch_count.restype = ll
     lib.fl_launch_count.argtypes = [vp]
     for name in EXPORTED:

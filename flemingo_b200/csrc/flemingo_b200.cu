@@ -50,6 +50,7 @@ static int fail(int code, const char *fmt, ...) {
 
 #include "place_kernel.cuh"
 #include "place_fast_kernel.cuh"
+#include "shape_bins_kernel.cuh"
 #include "fitness_kernel.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -135,7 +136,10 @@ struct SeqSet {
   bool valid = false;
   int n_seq = 0;
   std::vector<SeqClass> classes;
-  DevBuf packed, unk, word_off, unk_off, order, has_unk;
+  DevBuf packed, unk, word_off, unk_off, order, has_unk, d_len, bins;
+  int max_len = 0;
+  unsigned long long bins_signature = 0;  // shape-class signature the bins were computed for (0 = none)
+  long long bins_row_stride = 0;
   DevBuf E;  // energies [n_org][n_seq]
   int E_n_org = 0;
   bool E_valid = false;
@@ -145,16 +149,18 @@ struct Population {
   bool valid = false;
   int n_org = 0, n_rec_total = 0, max_rec = 0;
   std::vector<int> rec_begin, sum_len, con_M, pool_len;
+  int n_classes = 0, max_class_len = 0;
+  unsigned long long class_signature = 0;
   std::vector<int> kmer_need;  // ints of 4-mer tables if the organism is PSSM-only with >= 2 recognizers, else -1
   long long n_con = 0;
   int max_pool = 0, min_sum_len = 0;
-  DevBuf d_rec_begin, d_rec_type, d_rec_len, d_rec_nb, d_rec_data, d_pool_begin, d_rec_pool, d_con_M, d_con_pool, d_sum_len;
+  DevBuf d_rec_begin, d_rec_type, d_rec_len, d_rec_nb, d_rec_data, d_pool_begin, d_rec_pool, d_con_M, d_con_pool, d_sum_len, d_rec_class, d_cls_kind, d_cls_len, d_cls_nb, d_cls_edges, d_edges_pool;
 };
 
 struct fl_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  DevBuf tables, err_flag, con_begin, org_list, gaps, rsc, csc, fit_out, fit_scratch, fb_count, fb_pairs, fast_scratch;
+  DevBuf tables, err_flag, con_begin, org_list, gaps, rsc, csc, fit_out, fit_scratch, fb_count, fb_pairs, fast_scratch, fb_total;
   long long fast_pairs = 0, fallback_pairs = 0;  // statistics of the last fl_place_batch
   Population pop, scratch_pop;
   SeqSet sets[FL_MAX_SETS + 1];  // the extra slot serves fl_calculate
@@ -181,6 +187,8 @@ extern "C" int fl_ctx_create(int device, const double *tables, long long n_table
   int rc = ctx->tables.ensure(sizeof(double) * FL_N_TABLE_DOUBLES);
   if (rc == FL_OK) rc = ctx->err_flag.ensure(sizeof(int));
   if (rc == FL_OK) rc = ctx->fb_count.ensure(sizeof(int));
+  if (rc == FL_OK) rc = ctx->fb_total.ensure(sizeof(unsigned long long));
+  if (rc == FL_OK && cudaMemsetAsync(ctx->fb_total.p, 0, sizeof(unsigned long long), ctx->stream) != cudaSuccess) rc = fail(FL_E_CUDA, "memset failed");
   if (rc != FL_OK) {
     delete ctx;
     return rc;
@@ -202,7 +210,8 @@ extern "C" int fl_ctx_create(int device, const double *tables, long long n_table
 
 static void release_pop(Population &p) {
   DevBuf *bufs[] = {&p.d_rec_begin, &p.d_rec_type, &p.d_rec_len, &p.d_rec_nb, &p.d_rec_data,
-                    &p.d_pool_begin, &p.d_rec_pool, &p.d_con_M, &p.d_con_pool, &p.d_sum_len};
+                    &p.d_pool_begin, &p.d_rec_pool, &p.d_con_M, &p.d_con_pool, &p.d_sum_len,
+                    &p.d_rec_class, &p.d_cls_kind, &p.d_cls_len, &p.d_cls_nb, &p.d_cls_edges, &p.d_edges_pool};
   for (DevBuf *b : bufs) b->release();
 }
 
@@ -211,11 +220,11 @@ extern "C" int fl_ctx_destroy(fl_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (SeqSet &s : ctx->sets) {
-    s.packed.release(); s.unk.release(); s.word_off.release(); s.unk_off.release(); s.order.release(); s.has_unk.release(); s.E.release();
+    s.packed.release(); s.unk.release(); s.word_off.release(); s.unk_off.release(); s.order.release(); s.has_unk.release(); s.d_len.release(); s.bins.release(); s.E.release();
   }
   release_pop(ctx->pop);
   release_pop(ctx->scratch_pop);
-  DevBuf *bufs[] = {&ctx->tables, &ctx->err_flag, &ctx->con_begin, &ctx->org_list, &ctx->gaps, &ctx->rsc, &ctx->csc, &ctx->fit_out, &ctx->fit_scratch, &ctx->fb_count, &ctx->fb_pairs, &ctx->fast_scratch};
+  DevBuf *bufs[] = {&ctx->tables, &ctx->err_flag, &ctx->con_begin, &ctx->org_list, &ctx->gaps, &ctx->rsc, &ctx->csc, &ctx->fit_out, &ctx->fit_scratch, &ctx->fb_count, &ctx->fb_pairs, &ctx->fast_scratch, &ctx->fb_total};
   for (DevBuf *b : bufs) b->release();
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -295,7 +304,8 @@ static int upload_sequences(fl_ctx *ctx, SeqSet &set, const char *bytes, const l
   int rc;
   if ((rc = set.packed.ensure(packed.size() * 4)) || (rc = set.unk.ensure(unk.size() * 4)) ||
       (rc = set.word_off.ensure((size_t)n_seq * 4 + 4)) || (rc = set.unk_off.ensure((size_t)n_seq * 4 + 4)) ||
-      (rc = set.order.ensure((size_t)n_seq * 4 + 4)) || (rc = set.has_unk.ensure((size_t)n_seq + 4)))
+      (rc = set.order.ensure((size_t)n_seq * 4 + 4)) || (rc = set.has_unk.ensure((size_t)n_seq + 4)) ||
+      (rc = set.d_len.ensure((size_t)n_seq * 4 + 4)))
     return rc;
   CK(cudaMemcpyAsync(set.packed.p, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(set.unk.p, unk.data(), unk.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -304,8 +314,12 @@ static int upload_sequences(fl_ctx *ctx, SeqSet &set, const char *bytes, const l
     CK(cudaMemcpyAsync(set.unk_off.p, unk_off.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(set.order.p, order.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(set.has_unk.p, has_unk.data(), (size_t)n_seq, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(set.d_len.p, len.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, ctx->stream));
   }
   CK(cudaStreamSynchronize(ctx->stream));  // the staging vectors die at return
+  set.max_len = 0;
+  for (int s2 = 0; s2 < n_seq; ++s2) set.max_len = std::max(set.max_len, len[s2]);
+  set.bins_signature = 0;
   set.valid = true;
   set.E_valid = false;
   return FL_OK;
@@ -363,22 +377,68 @@ static int upload_population(fl_ctx *ctx, Population &P, const fl_population *po
     P.sum_len[o] = sl;
     P.pool_len[o] = (int)(pop->pool_begin[o + 1] - pop->pool_begin[o]);
     {
+      // ints the integer fast path needs for this organism: 4-mer tables per PSSM, one bin table per shape recognizer
       int need = 0;
-      bool all_pssm = n >= 2;
-      for (int i = 0; i < n && all_pssm; ++i) {
+      for (int i = 0; i < n; ++i) {
         const char t = pop->rec_type[rb + i];
-        all_pssm = (t == 'p' || t == 'P');
-        need += 256 * ((pop->rec_len[rb + i] + 3) / 4);
+        need += (t == 'p' || t == 'P') ? 256 * ((pop->rec_len[rb + i] + 3) / 4) : pop->rec_nb[rb + i] - 1;
       }
-      P.kmer_need[o] = all_pssm ? need : -1;
+      P.kmer_need[o] = n >= 2 ? need : -1;
     }
     P.max_rec = std::max(P.max_rec, n);
     P.max_pool = std::max(P.max_pool, P.pool_len[o]);
     P.min_sum_len = std::min(P.min_sum_len, sl);
     if (n > 1 && P.con_M[o] < 1) return fail(FL_E_UNSUPPORTED, "organism %d: connectors without precomputed tables (legacy branch connector.c:70-72) are not supported", o);
   }
+  // shape classes
+  P.n_classes = pop->n_classes;
+  P.max_class_len = 0;
+  unsigned long long sig = 1469598103934665603ULL;
+  auto mix = [&sig](const void *data, size_t bytes) {
+    const unsigned char *b = static_cast<const unsigned char *>(data);
+    for (size_t i = 0; i < bytes; ++i) sig = (sig ^ b[i]) * 1099511628211ULL;
+  };
+  if (pop->n_classes < 0) return fail(FL_E_ARG, "fl_upload_population: negative n_classes");
+  for (int c = 0; c < pop->n_classes; ++c) {
+    const int nb = pop->cls_nb[c], L = pop->cls_len[c];
+    if (nb < 2 || nb > 256) return fail(FL_E_UNSUPPORTED, "shape class %d has %d bin edges (supported: 2..256)", c, nb);
+    if (L < 5) return fail(FL_E_ARG, "shape class %d has length %d", c, L);
+    if (pop->cls_edges[c] < 0 || pop->cls_edges[c] + nb > pop->n_edges) return fail(FL_E_ARG, "shape class %d: edges outside edges_pool", c);
+    P.max_class_len = std::max(P.max_class_len, L);
+    mix(&pop->cls_kind[c], 1);
+    mix(&L, sizeof L);
+    mix(&nb, sizeof nb);
+    mix(pop->edges_pool + pop->cls_edges[c], sizeof(double) * nb);
+  }
+  P.class_signature = pop->n_classes ? (sig | 1ULL) : 0ULL;
+  for (int r = 0; r < pop->n_rec_total; ++r) {
+    const char t = pop->rec_type[r];
+    const bool is_p = (t == 'p' || t == 'P');
+    const int cls = pop->rec_class ? pop->rec_class[r] : -1;
+    if (is_p) continue;
+    if (cls < 0 || cls >= pop->n_classes) return fail(FL_E_ARG, "recognizer %d: shape class %d out of range", r, cls);
+    if (pop->cls_len[cls] != pop->rec_len[r] || pop->cls_nb[cls] != pop->rec_nb[r])
+      return fail(FL_E_ARG, "recognizer %d does not match its shape class (length / number of edges)", r);
+  }
   int rc;
   const size_t nr = (size_t)pop->n_rec_total;
+  const size_t ncl = (size_t)pop->n_classes;
+  if ((rc = P.d_rec_class.ensure(nr * 4 + 4)) || (rc = P.d_cls_kind.ensure(ncl + 4)) || (rc = P.d_cls_len.ensure(ncl * 4 + 4)) ||
+      (rc = P.d_cls_nb.ensure(ncl * 4 + 4)) || (rc = P.d_cls_edges.ensure(ncl * 8 + 8)) || (rc = P.d_edges_pool.ensure((size_t)pop->n_edges * 8 + 8)))
+    return rc;
+  {
+    std::vector<int> cls_of(nr, -1);
+    if (pop->rec_class) cls_of.assign(pop->rec_class, pop->rec_class + nr);
+    if (nr) CK(cudaMemcpyAsync(P.d_rec_class.p, cls_of.data(), nr * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (ncl) {
+      CK(cudaMemcpyAsync(P.d_cls_kind.p, pop->cls_kind, ncl, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(P.d_cls_len.p, pop->cls_len, ncl * 4, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(P.d_cls_nb.p, pop->cls_nb, ncl * 4, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(P.d_cls_edges.p, pop->cls_edges, ncl * 8, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(P.d_edges_pool.p, pop->edges_pool, (size_t)pop->n_edges * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
   if ((rc = P.d_rec_begin.ensure((n_org + 1) * 4)) || (rc = P.d_rec_type.ensure(nr + 4)) || (rc = P.d_rec_len.ensure(nr * 4 + 4)) ||
       (rc = P.d_rec_nb.ensure(nr * 4 + 4)) || (rc = P.d_rec_data.ensure(nr * 8 + 8)) || (rc = P.d_pool_begin.ensure((n_org + 1) * 8)) ||
       (rc = P.d_rec_pool.ensure((size_t)pop->n_pool * 8 + 8)) || (rc = P.d_con_M.ensure((size_t)n_org * 4 + 4)) ||
@@ -469,6 +529,35 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
   int n_sm = 148;
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
 
+  // ---- shape bins of this dataset for the population's shape classes (once per dataset / class set) ----------
+  if (P.n_classes > 0 && set.bins_signature != P.class_signature) {
+    set.bins_row_stride = (set.max_len + 15) & ~15LL;
+    if ((rc = set.bins.ensure((size_t)P.n_classes * n_seq * (size_t)set.bins_row_stride))) return rc;
+    ShapeBinParams q;
+    q.packed = set.packed.as<unsigned>();
+    q.word_off = set.word_off.as<int>();
+    q.seq_len = set.d_len.as<int>();
+    q.n_seq = n_seq;
+    q.cls_kind = P.d_cls_kind.as<char>();
+    q.cls_len = P.d_cls_len.as<int>();
+    q.cls_nb = P.d_cls_nb.as<int>();
+    q.cls_edges = P.d_cls_edges.as<long long>();
+    q.edges_pool = P.d_edges_pool.as<double>();
+    q.tables = ctx->tables.as<double>();
+    q.bins = set.bins.as<unsigned char>();
+    q.row_stride = set.bins_row_stride;
+    for (int c0 = 0; c0 < P.n_classes; c0 += 65535) {  // gridDim.y limit
+      ShapeBinParams qq = q;
+      qq.cls_kind += c0; qq.cls_len += c0; qq.cls_nb += c0; qq.cls_edges += c0;
+      qq.bins += (size_t)c0 * n_seq * (size_t)set.bins_row_stride;
+      const int ny = std::min(65535, P.n_classes - c0);
+      shape_bins_kernel<<<dim3((unsigned)n_seq, (unsigned)ny), 128, 0, ctx->stream>>>(qq);
+      CK(cudaGetLastError());
+      ctx->launches++;
+    }
+    set.bins_signature = P.class_signature;
+  }
+
   for (int c = 0; c < n_cls; ++c) {
     const SeqClass &cl = set.classes[c];
     PlaceParams pp;
@@ -493,6 +582,9 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
     pp.S = cl.len;
     pp.n_seq_total = n_seq;
     pp.tables = ctx->tables.as<double>();
+    pp.rec_class = P.d_rec_class.as<int>();
+    pp.bins = set.bins.as<unsigned char>();
+    pp.bins_row_stride = set.bins_row_stride;
     pp.E = set.E.as<double>();
     pp.gaps = ctx->gaps.as<int>();
     pp.rsc = ctx->rsc.as<double>();
@@ -606,6 +698,7 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
     }
     if (n_fast_org > 0) {
       const long long cap = n_fast_org * cl.count;
+      ctx->fast_pairs += cap;
       if ((rc = ctx->fb_pairs.ensure((size_t)cap * sizeof(int2)))) return rc;
       fp.fb_count = ctx->fb_count.as<int>();
       fp.fb_pairs = ctx->fb_pairs.as<int2>();
@@ -642,9 +735,9 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
                            sizeof(RecDesc) * P.max_rec + (size_t)lp.code_stride;
       const unsigned lgrid = (unsigned)std::min<long long>(cap, (long long)n_sm * 16);
       if (trace)
-        place_list_kernel<true><<<lgrid, 32, lsmem, ctx->stream>>>(lp, fp.fb_count, fp.fb_pairs);
+        place_list_kernel<true><<<lgrid, 32, lsmem, ctx->stream>>>(lp, fp.fb_count, fp.fb_pairs, ctx->fb_total.as<unsigned long long>());
       else
-        place_list_kernel<false><<<lgrid, 32, lsmem, ctx->stream>>>(lp, fp.fb_count, fp.fb_pairs);
+        place_list_kernel<false><<<lgrid, 32, lsmem, ctx->stream>>>(lp, fp.fb_count, fp.fb_pairs, ctx->fb_total.as<unsigned long long>());
       CK(cudaGetLastError());
       ctx->launches++;
     }
@@ -668,6 +761,19 @@ extern "C" int fl_place_batch(fl_ctx *ctx, int set_id, const long long *con_begi
   if (set_id < 0 || set_id >= FL_MAX_SETS) return fail(FL_E_ARG, "fl_place_batch: set_id %d out of range", set_id);
   CK(cudaSetDevice(ctx->device));
   return place_batch(ctx, ctx->pop, ctx->sets[set_id], con_begin, flags, energies, gaps, rec_scores, con_scores);
+}
+
+extern "C" int fl_path_stats(fl_ctx *ctx, long long *fast_pairs, long long *fallback_pairs) {
+  if (!ctx) return fail(FL_E_ARG, "fl_path_stats: null context");
+  CK(cudaSetDevice(ctx->device));
+  unsigned long long fb = 0;
+  CK(cudaMemcpyAsync(&fb, ctx->fb_total.p, sizeof fb, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (fast_pairs) *fast_pairs = ctx->fast_pairs;
+  if (fallback_pairs) *fallback_pairs = (long long)fb;
+  ctx->fast_pairs = 0;
+  CK(cudaMemsetAsync(ctx->fb_total.p, 0, sizeof fb, ctx->stream));
+  return FL_OK;
 }
 
 extern "C" int fl_fitness(fl_ctx *ctx, int pos_set, int neg_set, int method, double gamma, double *out) {
@@ -712,9 +818,10 @@ extern "C" int fl_calculate(fl_ctx *ctx, const char *sequence, int seq_len, cons
   if (n_rec > 1 && (M < 1 || n_con_doubles != (long long)(n_rec - 1) * (2LL * M + 2)))
     return fail(FL_E_ARG, "fl_calculate: con_matrices has %lld doubles, expected %lld for max_length %d", n_con_doubles, (long long)(n_rec - 1) * (2LL * M + 2), max_length);
   // build a one-organism population
-  std::vector<double> pool;
-  std::vector<long long> rec_data(n_rec);
-  std::vector<int> rec_nb(n_rec, 0);
+  std::vector<double> pool, edges_pool;
+  std::vector<long long> rec_data(n_rec), cls_edges;
+  std::vector<int> rec_nb(n_rec, 0), rec_class(n_rec, -1), cls_len, cls_nb;
+  std::vector<char> cls_kind;
   long long m_off = 0, a_off = 0, e_off = 0;
   int shape_i = 0;
   for (int i = 0; i < n_rec; ++i) {
@@ -732,6 +839,12 @@ extern "C" int fl_calculate(fl_ctx *ctx, const char *sequence, int seq_len, cons
       rec_nb[i] = nb;
       pool.insert(pool.end(), bin_freqs + a_off, bin_freqs + a_off + 2LL * (nb - 1));  // null ++ alt (organism.c:159-172)
       pool.insert(pool.end(), bin_edges + e_off, bin_edges + e_off + nb);
+      rec_class[i] = (int)cls_kind.size();
+      cls_kind.push_back(rec_types[i]);
+      cls_len.push_back(L);
+      cls_nb.push_back(nb);
+      cls_edges.push_back((long long)edges_pool.size());
+      edges_pool.insert(edges_pool.end(), bin_edges + e_off, bin_edges + e_off + nb);
       a_off += 2LL * (nb - 1);
       e_off += nb;
       ++shape_i;
@@ -754,6 +867,14 @@ extern "C" int fl_calculate(fl_ctx *ctx, const char *sequence, int seq_len, cons
   pop.con_M = &con_M;
   pop.con_pool = con_matrices;
   pop.n_con = n_rec > 1 ? n_con_doubles : 0;
+  pop.rec_class = rec_class.data();
+  pop.n_classes = (int)cls_kind.size();
+  pop.cls_kind = cls_kind.data();
+  pop.cls_len = cls_len.data();
+  pop.cls_nb = cls_nb.data();
+  pop.cls_edges = cls_edges.data();
+  pop.edges_pool = edges_pool.data();
+  pop.n_edges = (long long)edges_pool.size();
   int rc = upload_population(ctx, ctx->scratch_pop, &pop);
   if (rc) return rc;
   SeqSet &set = ctx->sets[FL_MAX_SETS];

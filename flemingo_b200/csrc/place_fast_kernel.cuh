@@ -22,6 +22,7 @@
 #pragma once
 
 constexpr int kCandCap = 16;   // candidates kept per stage before a pair is handed to the exact kernel
+constexpr int kNanBinMarker = (int)0x80000000;  // quantised score of a bin whose null frequency is NaN
 constexpr int kSlackUnits = 2; // covers fp64-vs-real rounding of the reference sums (<< 1 unit) with margin
 
 struct FastParams {
@@ -47,8 +48,9 @@ struct FastPlan {
   int ok;                                // 0: this organism cannot use the integer pass
   int thr_final;                         // slack on the last row
   int thr_pred[FL_MAX_RECOGNIZERS];      // slack on predecessor scans of stage i
-  int ngroups[FL_MAX_RECOGNIZERS];       // 4-mer groups of recognizer i
-  int kmer_off[FL_MAX_RECOGNIZERS];      // offset of its tables in s_kmer
+  int ngroups[FL_MAX_RECOGNIZERS];       // 4-mer groups of PSSM recognizer i (0 for a shape recognizer)
+  int kmer_off[FL_MAX_RECOGNIZERS];      // offset of its tables in s_kmer (4-mer tables, or nb-1 quantised bin scores)
+  int err_half[FL_MAX_RECOGNIZERS];      // rounded table entries on a path through recognizer i (half units of error)
 };
 
 struct FastSmem {
@@ -122,6 +124,21 @@ __device__ __forceinline__ double score_exact_packed(const RecDesc &r, const dou
   return s;
 }
 
+// quantised score of recognizer r at relative offset j: 4-mer tables for a PSSM, bin table for a shape recognizer
+__device__ __forceinline__ int score_q_any(const FastPlan &plan, int r, const RecDesc &rd, const int *__restrict__ kmer,
+                                           const unsigned *__restrict__ w, const unsigned char *__restrict__ bins_seq,
+                                           size_t cls_stride, int j) {
+  if (rd.kind == 0) return score_q(kmer + plan.kmer_off[r], plan.ngroups[r], w, rd.fwd + j);
+  return kmer[plan.kmer_off[r] + bins_seq[(size_t)rd.cls * cls_stride + rd.fwd + j]];
+}
+// exact score of recognizer rd at relative offset j
+__device__ __forceinline__ double score_exact_any(const RecDesc &rd, const double *s_pool, const unsigned *w,
+                                                  const unsigned char *__restrict__ bins_seq, size_t cls_stride, int j) {
+  if (rd.kind == 0) return score_exact_packed(rd, s_pool, w, rd.fwd + j);
+  int dummy = 0;  // a NaN null model keeps the organism off this path (build_fast_plan), so nothing to flag here
+  return score_shape_bin(rd, s_pool, bins_seq[(size_t)rd.cls * cls_stride + rd.fwd + j], dummy);
+}
+
 // ---- quantisation plan of one organism (executed by warp 0 after the exact tables are in shared memory) ----
 __device__ void build_fast_plan(const FastParams &f, const OrgView &v, const FastSmem &sm, int lane) {
   const PlaceParams &p = f.base;
@@ -136,20 +153,41 @@ __device__ void build_fast_plan(const FastParams &f, const OrgView &v, const Fas
     const RecDesc rd = sm.rec[r];
     const double *m = sm.pool + rd.data;
     double lo = 0.0, hi = 0.0;
-    for (int c = lane; c < rd.len; c += 32) {
-      lo += fmin(fmin(m[4 * c], m[4 * c + 1]), fmin(m[4 * c + 2], m[4 * c + 3]));
-      hi += fmax(fmax(m[4 * c], m[4 * c + 1]), fmax(m[4 * c + 2], m[4 * c + 3]));
-      bad |= (m[4 * c] != m[4 * c]) | (m[4 * c + 1] != m[4 * c + 1]) | (m[4 * c + 2] != m[4 * c + 2]) | (m[4 * c + 3] != m[4 * c + 3]);
-    }
+    if (rd.kind == 0) {
+      for (int c = lane; c < rd.len; c += 32) {
+        lo += fmin(fmin(m[4 * c], m[4 * c + 1]), fmin(m[4 * c + 2], m[4 * c + 3]));
+        hi += fmax(fmax(m[4 * c], m[4 * c + 1]), fmax(m[4 * c + 2], m[4 * c + 3]));
+        bad |= (m[4 * c] != m[4 * c]) | (m[4 * c + 1] != m[4 * c + 1]) | (m[4 * c + 2] != m[4 * c + 2]) | (m[4 * c + 3] != m[4 * c + 3]);
+      }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      lo += __shfl_xor_sync(0xffffffffu, lo, o);
-      hi += __shfl_xor_sync(0xffffffffu, hi, o);
+      for (int o = 16; o > 0; o >>= 1) {
+        lo += __shfl_xor_sync(0xffffffffu, lo, o);
+        hi += __shfl_xor_sync(0xffffffffu, hi, o);
+      }
+      kmer_need += 256 * ((rd.len + 3) >> 2);
+    } else {
+      // shape: alt[b] - null[b] over all bins (the bin actually selected varies per offset)
+      lo = inf;
+      hi = -inf;
+      // A NaN null bin (an empty bin of the null histogram) is never selected by a real k-mer; if it ever is, the
+      // reference exits.  Such bins are left out of the range and carry a marker that sends the pair to the exact
+      // kernel, which reports the error.
+      for (int b = lane; b < rd.nb - 1; b += 32) {
+        double x = m[(rd.nb - 1) + b] - m[b];
+        bad |= (m[(rd.nb - 1) + b] != m[(rd.nb - 1) + b]);
+        if (x != x) continue;
+        if (x < BIG_NEG) x = BIG_NEG;
+        lo = fmin(lo, x);
+        hi = fmax(hi, x);
+      }
+      lo = warp_min(lo);
+      hi = warp_max(hi);
+      if (!(lo <= hi)) bad = true;  // every bin is NaN
+      kmer_need += rd.nb - 1;
     }
     lo_sum += lo;
     hi_sum += hi;
     range += hi - lo;
-    kmer_need += 256 * ((rd.len + 3) >> 2);
   }
   for (int c = 0; c < n - 1; ++c) {
     const ConView cvw = connector_view(p, v, c);
@@ -187,10 +225,36 @@ __device__ void build_fast_plan(const FastParams &f, const OrgView &v, const Fas
     for (int r = 0; r < n; ++r) {
       const RecDesc rd = sm.rec[r];
       const double *m = sm.pool + rd.data;
+      if (rd.kind != 0) {
+        if (lane == 0) {
+          plan->ngroups[r] = 0;
+          plan->kmer_off[r] = off;
+          plan->err_half[r] = 1;
+        }
+        int lo = 0x7fffffff, hi = -0x7fffffff;
+        for (int b = lane; b < rd.nb - 1; b += 32) {
+          double x = m[(rd.nb - 1) + b] - m[b];
+          if (x != x) {
+            sm.kmer[off + b] = kNanBinMarker;
+            continue;
+          }
+          if (x < BIG_NEG) x = BIG_NEG;
+          const int q = __double2int_rn(x * s);
+          sm.kmer[off + b] = q;
+          lo = min(lo, q);
+          hi = max(hi, q);
+        }
+        lo_q += warp_min_i(lo);
+        hi_q += warp_max_i(hi);
+        off += rd.nb - 1;
+        groups_total += 1;
+        continue;
+      }
       const int ng = (rd.len + 3) >> 2;
       if (lane == 0) {
         plan->ngroups[r] = ng;
         plan->kmer_off[r] = off;
+        plan->err_half[r] = ng;
       }
       for (int g = 0; g < ng; ++g) {
         int lo = 0x7fffffff, hi = -0x7fffffff;
@@ -253,7 +317,7 @@ __device__ void build_fast_plan(const FastParams &f, const OrgView &v, const Fas
     for (int i = 0; i < n; ++i) {
       // predecessors of stage i: values Cq_{i-1}[k] + Gq  ->  err_{i-1} + 0.5
       plan->thr_pred[i] = half_units + 1 + 2 * kSlackUnits;   // 2 * (err_{i-1} + 0.5) = half_units + 1   (i >= 1)
-      half_units += plan->ngroups[i] + (i > 0 ? 1 : 0);
+      half_units += plan->err_half[i] + (i > 0 ? 1 : 0);
     }
     plan->thr_final = half_units + 2 * kSlackUnits;          // 2 * err_{n-1}
   }
@@ -279,6 +343,8 @@ __device__ bool refine_pair(const FastParams &f, const OrgView &v, const FastSme
   double *cr = sm.cr + (size_t)warp * p.max_rec * kCandCap;
   unsigned *bitmap = sm.bitmap + (size_t)warp * f.bitmap_words;
   const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned char *bins_seq = p.bins + (size_t)seq * p.bins_row_stride;
+  const size_t cls_stride = (size_t)p.n_seq_total * p.bins_row_stride;
 
   // (1) candidates on the last row
   {
@@ -310,12 +376,11 @@ __device__ bool refine_pair(const FastParams &f, const OrgView &v, const FastSme
     const int *prev = row_q(f, n, i - 1, rowsq, rowsg);
     const int *cur = row_q(f, n, i, rowsq, rowsg);
     const int *Gq = sm.Gq + (size_t)(i - 1) * f.gq_stride + kGPad;
-    const int *tab = sm.kmer + plan.kmer_off[i];
-    const int fwd = sm.rec[i].fwd;
+    const RecDesc rdi = sm.rec[i];
     const int cnt = cn[i];
     for (int c = 0; c < cnt; ++c) {
       const int j = cj[i * kCandCap + c];
-      const int thr = (cur[j] - score_q(tab, plan.ngroups[i], w, fwd + j)) - plan.thr_pred[i];
+      const int thr = (cur[j] - score_q_any(plan, i, rdi, sm.kmer, w, bins_seq, cls_stride, j)) - plan.thr_pred[i];
       for (int base = 0; base <= j; base += 32) {
         const int k = base + lane;
         const bool pred = (k <= j) && (prev[k] + Gq[j - k] >= thr);
@@ -340,7 +405,7 @@ __device__ bool refine_pair(const FastParams &f, const OrgView &v, const FastSme
   }
   // (3) exact forward evaluation on the candidate sets (lane = one candidate of the stage)
   if (lane < cn[0]) {
-    const double r0 = score_exact_packed(sm.rec[0], sm.pool, w, cj[lane]);
+    const double r0 = score_exact_any(sm.rec[0], sm.pool, w, bins_seq, cls_stride, cj[lane]);
     cv[lane] = r0;
     cr[lane] = r0;
   }
@@ -349,7 +414,7 @@ __device__ bool refine_pair(const FastParams &f, const OrgView &v, const FastSme
     if (lane < cn[i]) {
       const int j = cj[i * kCandCap + lane];
       const RecDesc rd = sm.rec[i];
-      const double rj = score_exact_packed(rd, sm.pool, w, rd.fwd + j);
+      const double rj = score_exact_any(rd, sm.pool, w, bins_seq, cls_stride, j);
       const ConView cvw = connector_view(p, v, i - 1);
       double best = neg_inf();
       int arg = -1;
@@ -430,18 +495,24 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
     const int si = min(sbase + team, last - 1);
     const bool live = (sbase + team) < last;
     const int seq = p.order[p.class_begin + si];
-    const bool decline = !plan.ok || f.has_unk[seq];
+    bool decline = !plan.ok || f.has_unk[seq];
+    bool nan_hit = false;
     // ---- phase 1: integer pass ---------------------------------------------------------------------
     if (plan.ok) {
       const unsigned *pw = p.packed + p.word_off[seq];
       for (int t = tl; t < f.seqw_stride; t += TEAM) w[t] = (t < nwords) ? __ldg(pw + t) : 0u;
       __syncwarp();
+      const unsigned char *bins_seq = p.bins + (size_t)seq * p.bins_row_stride;
+      const size_t cls_stride = (size_t)p.n_seq_total * p.bins_row_stride;
       {
-        const int *tab = sm.kmer + plan.kmer_off[0];
-        const int ng = plan.ngroups[0];
+        const RecDesc rd0 = sm.rec[0];
         const bool spill = 0 <= n - 3;
         for (int j = tl; j < P + J; j += TEAM) {
-          const int x = (j < P) ? score_q(tab, ng, w, j) : 0;
+          int x = (j < P) ? score_q_any(plan, 0, rd0, sm.kmer, w, bins_seq, cls_stride, j) : 0;
+          if (x == kNanBinMarker) {
+            nan_hit = true;
+            x = 0;
+          }
           rowsq[j] = x;
           if (spill && j < P) rowsg[j] = x;
         }
@@ -453,18 +524,26 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
         const int *Gq = sm.Gq + (size_t)(i - 1) * f.gq_stride + kGPad;
         dp_stage<J, TEAM, OpI32>(prev, cur, Gq, P, tl, plan.sent);
         __syncwarp();
-        const int *tab = sm.kmer + plan.kmer_off[i];
-        const int ng = plan.ngroups[i];
-        const int fwd = sm.rec[i].fwd;
+        const RecDesc rdi = sm.rec[i];
         const bool spill = i <= n - 3;
         int *gl = rowsg + (size_t)i * f.rowq_stride;
         for (int j = tl; j < P + J; j += TEAM) {
-          const int x = (j < P) ? cur[j] + score_q(tab, ng, w, fwd + j) : 0;
+          int r = (j < P) ? score_q_any(plan, i, rdi, sm.kmer, w, bins_seq, cls_stride, j) : 0;
+          if (r == kNanBinMarker) {
+            nan_hit = true;
+            r = 0;
+          }
+          const int x = (j < P) ? cur[j] + r : 0;
           cur[j] = x;
           if (spill && j < P) gl[j] = x;
         }
         __syncwarp();
       }
+    }
+    // a selected NaN-null bin: the pair goes to the exact kernel, which raises the reference's error
+    {
+      const unsigned hit = __ballot_sync(0xffffffffu, nan_hit);
+      if ((hit >> (team * TEAM)) & ((TEAM == 32) ? 0xffffffffu : ((1u << TEAM) - 1u))) decline = true;
     }
     // ---- phase 2: exact refinement, one pair after the other, whole warp ---------------------------------
     for (int t = 0; t < NT; ++t) {

@@ -39,7 +39,7 @@ struct RecDesc {
   int nb;    // number of bin edges (shape only)
   int data;  // offset into the organism's slice of the recognizer pool (doubles)
   int fwd;   // sum of the lengths of the recognizers before this one (organism.c:273,392)
-  int pad;
+  int cls;   // shape class (index into the precomputed bin rows), -1 for a PSSM
 };
 
 struct PlaceParams {
@@ -63,8 +63,11 @@ struct PlaceParams {
   const int *unk_off;
   const int *order;
   int class_begin, class_count, S, n_seq_total;
-  // data tables
+  // data tables and precomputed shape bins (shape_bins_kernel.cuh)
   const double *tables;
+  const int *rec_class;           // [n_rec_total] shape class of a recognizer, -1 for PSSM
+  const unsigned char *bins;      // [class][seq][bins_row_stride] bin index per offset
+  long long bins_row_stride;
   // outputs
   double *E;
   int *gaps;
@@ -81,65 +84,25 @@ __device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xfff0
 
 __device__ __forceinline__ int code0(unsigned char c) { return (c & 3) * (c < 4); }
 
-// Score of one recognizer at one offset.  `codes` already points at the recognizer's first admissible base
-// (sequence + forward offset, organism.c:328).  Codes: 0..3 = A,G,C,T; 4 = any other byte.
-__device__ __noinline__ double score_shape(const RecDesc &r, const double *s_pool, const unsigned char *c,
-                                           const double *__restrict__ tables, int &err) {
-  const int np = r.len - 4;
-  double score;
-  // pentamer index: sum code * 4^(4-k), unknown bytes count as 0 (recognizer.c:219-241 has no default case)
-  int idx = 0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) idx = idx * 4 + code0(c[k]);
-  if (r.kind <= 2) {
-    // _aux.c:211-217
-    const double *tab = tables + (r.kind == 1 ? T_MGW : T_PROT);
-    double sum = 0.0;
-    for (int j = 0; j < np; ++j) {
-      idx = ((idx << 2) | code0(c[j + 4])) & 1023;
-      sum += __ldg(tab + idx);
-    }
-    score = sum / (double)np;
-  } else {
-    // _aux.c:203-209 on pent = [TAB[idx_0..]] ++ [TAB[1024+idx_0..]] (recognizer.c:447-450)
-    const double *tab = tables + (r.kind == 3 ? T_ROLL : T_HELT);
-    const int idx0 = ((idx << 2) | code0(c[4])) & 1023;
-    int idxl = 0;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) idxl = idxl * 4 + code0(c[np - 1 + k]);
-    double sum = __ldg(tab + idx0) + __ldg(tab + 1024 + idxl);
-    int id = idx;
-    for (int j = 0; j < np; ++j) {
-      id = ((id << 2) | code0(c[j + 4])) & 1023;
-      sum += __ldg(tab + id);
-    }
-    id = idx;
-    for (int j = 0; j < np; ++j) {
-      id = ((id << 2) | code0(c[j + 4])) & 1023;
-      sum += __ldg(tab + 1024 + id);
-    }
-    score = sum / (double)(2 * np + 2);
-  }
-  // _aux.c:184-190: first bin with edges[b-1] <= score < edges[b], otherwise the last bin
+// Score of a shape recognizer from its precomputed bin (recognizer.c:246-262): alt[b] - null[b], floored at -1e10;
+// selecting a NaN null bin is the error the reference exits on.
+__device__ __forceinline__ double score_shape_bin(const RecDesc &r, const double *s_pool, int b, int &err) {
   const double *nullf = s_pool + r.data;
-  const double *altf = nullf + (r.nb - 1);
-  const double *edges = altf + (r.nb - 1);
-  int b = 1;
-  for (; b < r.nb; ++b)
-    if (score >= edges[b - 1] && score < edges[b]) break;
-  if (b == r.nb) b = r.nb - 1;
-  const double n0 = nullf[b - 1];
-  double v = altf[b - 1] - n0;
+  const double n0 = nullf[b];
+  double v = nullf[(r.nb - 1) + b] - n0;
   if (v < BIG_NEG) v = BIG_NEG;
   if (n0 != n0) err |= ERR_NAN_NULL;
   return v;
 }
 
+// Score of one recognizer at offset `pos` (relative to its forward offset, organism.c:328).
+// codes: the sequence as byte codes (0..3 = A,G,C,T; 4 = any other byte); bins_seq: this sequence's bin rows
+// (class 0), cls_stride: distance between classes.
 __device__ __forceinline__ double score_rec(const RecDesc &r, const double *s_pool, const unsigned char *codes, int pos,
-                                            const double *__restrict__ tables, int &err) {
-  const unsigned char *c = codes + pos;
+                                            const unsigned char *__restrict__ bins_seq, size_t cls_stride, int &err) {
   if (r.kind == 0) {
     // recognizer.c:130-168: left-to-right sum from 0.0; an unknown byte adds nothing
+    const unsigned char *c = codes + r.fwd + pos;
     const double *m = s_pool + r.data;
     double s = 0.0;
     for (int col = 0; col < r.len; ++col) {
@@ -148,7 +111,7 @@ __device__ __forceinline__ double score_rec(const RecDesc &r, const double *s_po
     }
     return s;
   }
-  return score_shape(r, s_pool, c, tables, err);
+  return score_shape_bin(r, s_pool, bins_seq[(size_t)r.cls * cls_stride + r.fwd + pos], err);
 }
 
 // connector.c:35-66 for one gap length; D = DEN_EXPANSION
@@ -339,7 +302,7 @@ __device__ __forceinline__ OrgView organism_prologue(const PlaceParams &p, int o
       d.nb = p.rec_nb[rb + i];
       d.data = (int)(p.rec_data[rb + i] - pb);
       d.fwd = fwd;
-      d.pad = 0;
+      d.cls = p.rec_class[rb + i];
       fwd += d.len;
       s_rec[i] = d;
     }
@@ -379,7 +342,9 @@ __device__ __forceinline__ void place_pair_exact(const PlaceParams &p, const Org
   __syncwarp();
 
   // ---- stage 0: C_0 = R_0 (organism.c:381-385) --------------------------------------------------
-  for (int j = lane; j < P; j += 32) rows[j] = score_rec(s_rec[0], s_pool, codes, j, p.tables, err);
+  const unsigned char *bins_seq = p.bins + (size_t)seq * p.bins_row_stride;
+  const size_t cls_stride = (size_t)p.n_seq_total * p.bins_row_stride;
+  for (int j = lane; j < P; j += 32) rows[j] = score_rec(s_rec[0], s_pool, codes, j, bins_seq, cls_stride, err);
   __syncwarp();
 
   // ---- stages 1..n-1: C_i[j] = max_k (C_{i-1}[k] + G[j-k]) + R_i[j] (organism.c:347-369) ----------
@@ -390,8 +355,7 @@ __device__ __forceinline__ void place_pair_exact(const PlaceParams &p, const Org
     dp_stage<J, 32, OpF64>(prev, cur, Gc, P, lane, neg_inf());
     __syncwarp();
     const RecDesc rd = s_rec[i];
-    const unsigned char *ci = codes + rd.fwd;
-    for (int j = lane; j < P; j += 32) cur[j] = cur[j] + score_rec(rd, s_pool, ci, j, p.tables, err);
+    for (int j = lane; j < P; j += 32) cur[j] = cur[j] + score_rec(rd, s_pool, codes, j, bins_seq, cls_stride, err);
     __syncwarp();
   }
 
@@ -420,7 +384,7 @@ __device__ __forceinline__ void place_pair_exact(const PlaceParams &p, const Org
       const double *prev = rows + (size_t)(i - 1) * p.row_stride;
       const double *Gc = s_G + (size_t)(i - 1) * p.g_stride + kGPad;
       const RecDesc rd = s_rec[i];
-      const double ri = score_rec(rd, s_pool, codes + rd.fwd, m, p.tables, err);
+      const double ri = score_rec(rd, s_pool, codes, m, bins_seq, cls_stride, err);
       const double target = rows[(size_t)i * p.row_stride + m];
       int found = -1;
       for (int kb = 0; kb <= m && found < 0; kb += 32) {
@@ -489,10 +453,11 @@ __global__ void __launch_bounds__(256) place_tiled_kernel(const PlaceParams p) {
 // ------------------------------------------------------------------------------------------------
 template <bool TRACE>
 __global__ void __launch_bounds__(32) place_list_kernel(const PlaceParams p, const int *__restrict__ fb_count,
-                                                        const int2 *__restrict__ fb_pairs) {
+                                                        const int2 *__restrict__ fb_pairs, unsigned long long *fb_total) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const ExactSmem sm = carve_exact(p, smem_raw, 1);
   const int count = *fb_count;
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(fb_total, (unsigned long long)count);
   int err = 0;
   for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
     const int2 pr = fb_pairs[idx];

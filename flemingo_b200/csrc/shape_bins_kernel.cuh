@@ -1,0 +1,83 @@
+// shape_bins_kernel.cuh -- batched shape scoring, the organism-independent half of K1.
+//
+// A shape recognizer's score at an offset is alt[b] - null[b], where the bin b depends only on
+// (shape kind, recognizer length, bin edges, sequence, offset): the averaged pentamer score is binned against the
+// edges (recognizer.c:187-589, _aux.c:184-217).  Edges come from the null model of (kind, length), so a whole
+// population shares a handful of "shape classes".  This kernel evaluates every class on every sequence ONCE per
+// dataset, in exact double arithmetic and the reference's summation order (the binning is discontinuous, so the
+// average must be bit-identical), and stores the bin index as one byte per offset.  The placement kernels then
+// score a shape recognizer with a 1-byte load and a table lookup.
+#pragma once
+
+struct ShapeBinParams {
+  const unsigned *packed;    // 2-bit bases; non-ACGT bytes are stored as code 0, which is what the reference's
+  const int *word_off;       // pentamer index does with them (recognizer.c:219-241 has no default case)
+  const int *seq_len;
+  int n_seq;
+  const char *cls_kind;      // 'm','t','r','h'
+  const int *cls_len;
+  const int *cls_nb;         // number of bin edges
+  const long long *cls_edges;  // offset into edges_pool
+  const double *edges_pool;
+  const double *tables;
+  unsigned char *bins;       // [class][seq][row_stride]
+  long long row_stride;
+};
+
+__global__ void __launch_bounds__(128) shape_bins_kernel(const ShapeBinParams q) {
+  __shared__ double s_edges[256];
+  const int seq = blockIdx.x, cls = blockIdx.y;
+  const char kind = q.cls_kind[cls];
+  const int L = q.cls_len[cls], nb = q.cls_nb[cls], np = L - 4;
+  const int S = q.seq_len[seq];
+  const double *edges = q.edges_pool + q.cls_edges[cls];
+  const bool in_smem = nb <= 256;
+  if (in_smem)
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) s_edges[i] = edges[i];
+  __syncthreads();
+  const double *e = in_smem ? s_edges : edges;
+  const unsigned *w = q.packed + q.word_off[seq];
+  unsigned char *out = q.bins + ((size_t)cls * q.n_seq + seq) * q.row_stride;
+  const bool two_step = (kind == 'r' || kind == 'R' || kind == 'h' || kind == 'H');
+  const double *tab = q.tables + ((kind == 'm' || kind == 'M') ? T_MGW : (kind == 't' || kind == 'T') ? T_PROT : (kind == 'r' || kind == 'R') ? T_ROLL : T_HELT);
+  for (int p = threadIdx.x; p + L <= S; p += blockDim.x) {
+    auto code = [&](int pos) { return (int)((__ldg(w + (pos >> 4)) >> (2 * (pos & 15))) & 3u); };
+    int idx = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) idx = idx * 4 + code(p + k);
+    double score;
+    if (!two_step) {
+      // _aux.c:211-217
+      double sum = 0.0;
+      for (int j = 0; j < np; ++j) {
+        idx = ((idx << 2) | code(p + j + 4)) & 1023;
+        sum += __ldg(tab + idx);
+      }
+      score = sum / (double)np;
+    } else {
+      // _aux.c:203-209 on pent = [TAB[idx_0..]] ++ [TAB[1024+idx_0..]] (recognizer.c:447-450)
+      const int idx0 = ((idx << 2) | code(p + 4)) & 1023;
+      int idxl = 0;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) idxl = idxl * 4 + code(p + np - 1 + k);
+      double sum = __ldg(tab + idx0) + __ldg(tab + 1024 + idxl);
+      int id = idx;
+      for (int j = 0; j < np; ++j) {
+        id = ((id << 2) | code(p + j + 4)) & 1023;
+        sum += __ldg(tab + id);
+      }
+      id = idx;
+      for (int j = 0; j < np; ++j) {
+        id = ((id << 2) | code(p + j + 4)) & 1023;
+        sum += __ldg(tab + 1024 + id);
+      }
+      score = sum / (double)(2 * np + 2);
+    }
+    // _aux.c:184-190: first bin with edges[b-1] <= score < edges[b], otherwise the last bin
+    int b = 1;
+    for (; b < nb; ++b)
+      if (score >= e[b - 1] && score < e[b]) break;
+    if (b == nb) b = nb - 1;
+    out[p] = (unsigned char)(b - 1);
+  }
+}

@@ -78,6 +78,12 @@ class Engine:
     def launch_count(self) -> int:
         return int(self._lib.fl_launch_count(self._ctx))
 
+    def path_stats(self) -> tuple[int, int]:
+        """(pairs sent to the integer filter pass, pairs it handed back to the exact kernel) since the last call."""
+        a, b = C.c_longlong(0), C.c_longlong(0)
+        _cabi.check(self._lib.fl_path_stats(self._ctx, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def sync(self):
         _cabi.check(self._lib.fl_sync(self._ctx))
 
@@ -116,6 +122,14 @@ class Engine:
         pop.con_M = _ptr(packed.con_M)
         pop.con_pool = _ptr(packed.con_pool)
         pop.n_con = int(packed.con_pool.size)
+        pop.rec_class = _ptr(packed.rec_class)
+        pop.n_classes = int(packed.cls_kind.size)
+        pop.cls_kind = _ptr(packed.cls_kind)
+        pop.cls_len = _ptr(packed.cls_len)
+        pop.cls_nb = _ptr(packed.cls_nb)
+        pop.cls_edges = _ptr(packed.cls_edges)
+        pop.edges_pool = _ptr(packed.edges_pool)
+        pop.n_edges = int(packed.edges_pool.size)
         _cabi.check(self._lib.fl_upload_population(self._ctx, C.byref(pop)))
         packed.uploaded_con_size = int(packed.con_pool.size)
         self._packed = packed

@@ -72,6 +72,13 @@ class PackedPopulation:
     con_base: np.ndarray      # int64 [n_org] offset of each organism's own tables in con_pool
     sum_len: np.ndarray       # int32 [n_org]
     pseudo_count: np.ndarray  # float64 [n_org] connector pseudo count
+    # shape classes: distinct (kind, length, edges) of the shape recognizers (fl_population.rec_class ...)
+    rec_class: np.ndarray = None      # int32 [n_rec_total], -1 for PSSM
+    cls_kind: np.ndarray = None       # uint8 [n_classes]
+    cls_len: np.ndarray = None        # int32 [n_classes]
+    cls_nb: np.ndarray = None         # int32 [n_classes]
+    cls_edges: np.ndarray = None      # int64 [n_classes]
+    edges_pool: np.ndarray = None     # float64
     ids: list = field(default_factory=list)
     # (organism index, sequence length) -> offset of the rescaled variant in con_pool
     variants: dict = field(default_factory=dict)
@@ -145,6 +152,8 @@ def pack_population(organisms) -> PackedPopulation:
     sum_len = np.zeros(n_org, dtype=np.int32)
     pcs = np.zeros(n_org, dtype=np.float64)
     types, lens, nbs, datas, pool_parts, con_parts, ids = [], [], [], [], [], [], []
+    classes, class_of, cls_kind, cls_len, cls_nb, cls_edges, edge_parts = {}, [], [], [], [], [], []
+    edge_off = 0
     pool_off = 0
     con_off = 0
     for o, org in enumerate(organisms):
@@ -172,11 +181,22 @@ def pack_population(organisms) -> PackedPopulation:
                 m_off += 4 * L
                 org_pool += 4 * L
                 nbs.append(0)
+                class_of.append(-1)
             else:
                 nb = int(bin_nums[shape_i])
                 # parse_org (organism.c:159-185): null = models+a, alt = models+a+(nb-1), edges = edges+e
                 org_parts.append(models[a_off:a_off + 2 * (nb - 1)])
                 org_parts.append(edges[e_off:e_off + nb])
+                key = (t.lower(), L, edges[e_off:e_off + nb].tobytes())
+                if key not in classes:
+                    classes[key] = len(classes)
+                    cls_kind.append(ord(t))
+                    cls_len.append(L)
+                    cls_nb.append(nb)
+                    cls_edges.append(edge_off)
+                    edge_parts.append(edges[e_off:e_off + nb])
+                    edge_off += nb
+                class_of.append(classes[key])
                 a_off += 2 * (nb - 1)
                 e_off += nb
                 org_pool += 3 * nb - 2
@@ -212,7 +232,11 @@ def pack_population(organisms) -> PackedPopulation:
         rec_data=np.asarray(datas, dtype=np.int64), pool_begin=pool_begin,
         rec_pool=np.ascontiguousarray(rec_pool, dtype=np.float64), con_M=con_M,
         con_pool=np.ascontiguousarray(con_pool, dtype=np.float64), con_base=con_base, sum_len=sum_len,
-        pseudo_count=pcs, ids=ids, n_base_con=int(con_pool.size))
+        pseudo_count=pcs, ids=ids, n_base_con=int(con_pool.size),
+        rec_class=np.asarray(class_of, dtype=np.int32), cls_kind=np.asarray(cls_kind, dtype=np.uint8),
+        cls_len=np.asarray(cls_len, dtype=np.int32), cls_nb=np.asarray(cls_nb, dtype=np.int32),
+        cls_edges=np.asarray(cls_edges, dtype=np.int64),
+        edges_pool=np.ascontiguousarray(np.concatenate(edge_parts) if edge_parts else np.zeros(0), dtype=np.float64))
 
 
 def placement_cost(packed: PackedPopulation, seq_len: int) -> np.ndarray:

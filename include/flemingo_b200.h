@@ -72,6 +72,17 @@ typedef struct fl_population {
                                   (organism_object.py:1490-1495); variants rescaled by adjust_scores
                                   (connector_object.py:454-487) are appended by the host */
   long long n_con;
+  /* shape classes: the distinct (kind, length, bin edges) among the population's shape recognizers.  The bin
+     an averaged shape score falls into depends only on the class, the sequence and the offset, so it is
+     computed once per dataset (recognizer.c:187-589, _aux.c:184-217) instead of once per organism. */
+  const int *rec_class;        /* [n_rec_total] class of a shape recognizer, -1 for 'p' */
+  int n_classes;
+  const char *cls_kind;        /* [n_classes] 'm','t','r','h' */
+  const int *cls_len;          /* [n_classes] recognizer length */
+  const int *cls_nb;           /* [n_classes] number of bin edges (<= 256) */
+  const long long *cls_edges;  /* [n_classes] offset of the class's edges in edges_pool */
+  const double *edges_pool;
+  long long n_edges;
 } fl_population;
 
 const char *fl_last_error(void);
@@ -137,6 +148,12 @@ int fl_calculate(fl_ctx *ctx, const char *sequence, int seq_len, const char *rec
                  const double *rec_matrices, const int *rec_lengths, const double *con_matrices,
                  long long n_con_doubles, double *rec_scores, double *con_scores, int *con_lengths, int max_length,
                  const double *bin_freqs, const double *bin_edges, const int *num_bins);
+
+/*
+ * Since the last call: pairs routed to the integer filter pass, and how many of those it handed back to the exact
+ * kernel (too many near-ties, unknown bytes, tables outside its fixed-point range).  Synchronises.
+ */
+int fl_path_stats(fl_ctx *ctx, long long *fast_pairs, long long *fallback_pairs);
 
 /* Counters for bench.py: kernels launched by this context since creation, and the last launch geometry. */
 long long fl_launch_count(fl_ctx *ctx);
