@@ -614,6 +614,7 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
     FastParams fp;
     fp.gq_stride = kGPad + Pmax + kGPad;
     fp.seqw_stride = (cl.len + 15) / 16 + 3;
+    fp.k8_stride = (cl.len + 7) & ~3;  // 4-mer codes of positions 0..S+2 (a partial last group overshoots by <= 3)
     fp.bitmap_words = (Pmax + 31) / 32 + 1;
     fp.want_trace = trace ? 1 : 0;
     fp.has_unk = set.has_unk.as<unsigned char>();
@@ -648,7 +649,7 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
         const size_t d = (size_t)pp.pool_stride + 2ull * nw * P.max_rec * kCandCap;
         const size_t i = (size_t)(P.max_rec - 1) * fp.gq_stride + fp.kmer_cap + (size_t)nw * nt * fast_slot[j] + (size_t)nw * nt * fp.seqw_stride +
                          2ull * nw * P.max_rec * kCandCap + (size_t)nw * P.max_rec + (size_t)nw * fp.bitmap_words;
-        const size_t bytes = d * 8 + i * 4 + sizeof(RecDesc) * P.max_rec + sizeof(FastPlan) + 16;
+        const size_t bytes = d * 8 + i * 4 + sizeof(RecDesc) * P.max_rec + sizeof(FastPlan) + 16 + (size_t)nw * nt * fp.k8_stride;
         if (bytes > (size_t)kMaxSmem) continue;
         const int ctas = (int)std::min<size_t>(233472 / (bytes + 1024), 32);
         const int occ = std::min(ctas * nw, 20);  // ~96 registers per thread cap residency at ~20 warps

@@ -35,6 +35,7 @@ struct FastParams {
   int rowq_stride;   // ints per quantised row
   int slotq_stride;  // ints per pair slot (2 ping-pong rows), == TEAM (mod 32) so that teams hit disjoint banks
   int seqw_stride;   // u32 words per packed sequence copy
+  int k8_stride;     // bytes per 4-mer code array (S + pad, multiple of 4)
   int kmer_cap;      // ints available for the 4-mer tables of one organism
   int bitmap_words;  // u32 words of the per-warp candidate bitmap
   int want_trace;
@@ -57,6 +58,7 @@ struct FastSmem {
   double *pool, *cv, *cr;
   int *Gq, *kmer, *rowsq, *cj, *ca, *cn;
   unsigned *seqw, *bitmap;
+  unsigned char *k8;
   RecDesc *rec;
   FastPlan *plan;
 };
@@ -77,6 +79,7 @@ __device__ __forceinline__ FastSmem carve_fast(const FastParams &f, unsigned cha
   s.ca = s.cj + (size_t)nwarps * p.max_rec * kCandCap;
   s.cn = s.ca + (size_t)nwarps * p.max_rec * kCandCap;
   s.bitmap = reinterpret_cast<unsigned *>(s.cn + (size_t)nwarps * p.max_rec);
+  s.k8 = reinterpret_cast<unsigned char *>(s.bitmap + (size_t)nwarps * f.bitmap_words);
   return s;
 }
 
@@ -105,14 +108,17 @@ __device__ __forceinline__ int warp_max_i(int v) {
 // base code (0..3) at position pos of a packed copy (16 bases per word, LSB first)
 __device__ __forceinline__ int packed_code(const unsigned *w, int pos) { return (w[pos >> 4] >> (2 * (pos & 15))) & 3; }
 
-// quantised PSSM score at `pos` (already including the recognizer's forward offset): one 4-mer lookup per group
-__device__ __forceinline__ int score_q(const int *__restrict__ tab, int ngroups, const unsigned *__restrict__ w, int pos) {
+// 8-bit code of the 4-mer starting at position q of a packed copy
+__device__ __forceinline__ unsigned kmer_code(const unsigned *__restrict__ w, int q) {
+  return __funnelshift_r(w[q >> 4], w[(q >> 4) + 1], 2 * (q & 15)) & 0xffu;
+}
+
+// quantised PSSM score at `pos` (already including the recognizer's forward offset): one 4-mer lookup per group.
+// k8[q] = code of the 4-mer starting at q, built once per pair (the same codes serve every recognizer and group).
+__device__ __forceinline__ int score_q(const int *__restrict__ tab, int ngroups, const unsigned char *__restrict__ k8, int pos) {
   int v = 0;
-  for (int g = 0; g < ngroups; ++g) {
-    const int q = pos + 4 * g;
-    const unsigned kmer = __funnelshift_r(w[q >> 4], w[(q >> 4) + 1], 2 * (q & 15)) & 0xffu;
-    v += tab[256 * g + kmer];
-  }
+  const unsigned char *k = k8 + pos;
+  for (int g = 0; g < ngroups; ++g) v += tab[256 * g + k[4 * g]];
   return v;
 }
 
@@ -126,9 +132,9 @@ __device__ __forceinline__ double score_exact_packed(const RecDesc &r, const dou
 
 // quantised score of recognizer r at relative offset j: 4-mer tables for a PSSM, bin table for a shape recognizer
 __device__ __forceinline__ int score_q_any(const FastPlan &plan, int r, const RecDesc &rd, const int *__restrict__ kmer,
-                                           const unsigned *__restrict__ w, const unsigned char *__restrict__ bins_seq,
+                                           const unsigned char *__restrict__ k8, const unsigned char *__restrict__ bins_seq,
                                            size_t cls_stride, int j) {
-  if (rd.kind == 0) return score_q(kmer + plan.kmer_off[r], plan.ngroups[r], w, rd.fwd + j);
+  if (rd.kind == 0) return score_q(kmer + plan.kmer_off[r], plan.ngroups[r], k8, rd.fwd + j);
   return kmer[plan.kmer_off[r] + bins_seq[(size_t)rd.cls * cls_stride + rd.fwd + j]];
 }
 // exact score of recognizer rd at relative offset j
@@ -332,7 +338,7 @@ __device__ __forceinline__ const int *row_q(const FastParams &f, int n, int i, c
 }
 
 __device__ bool refine_pair(const FastParams &f, const OrgView &v, const FastSmem &sm, const int *rowsq, const int *rowsg,
-                            const unsigned *w, int seq, int warp, int lane) {
+                            const unsigned *w, const unsigned char *k8, int seq, int warp, int lane) {
   const PlaceParams &p = f.base;
   const FastPlan &plan = *sm.plan;
   const int n = v.n, P = v.P;
@@ -371,50 +377,82 @@ __device__ bool refine_pair(const FastParams &f, const OrgView &v, const FastSme
   // (2) candidate sets of the earlier stages, top down
   const int words = (P + 31) >> 5;
   for (int i = n - 1; i >= 1; --i) {
-    for (int t = lane; t < words; t += 32) bitmap[t] = 0u;
-    __syncwarp();
     const int *prev = row_q(f, n, i - 1, rowsq, rowsg);
     const int *cur = row_q(f, n, i, rowsq, rowsg);
     const int *Gq = sm.Gq + (size_t)(i - 1) * f.gq_stride + kGPad;
     const RecDesc rdi = sm.rec[i];
     const int cnt = cn[i];
-    for (int c = 0; c < cnt; ++c) {
-      const int j = cj[i * kCandCap + c];
-      const int thr = (cur[j] - score_q_any(plan, i, rdi, sm.kmer, w, bins_seq, cls_stride, j)) - plan.thr_pred[i];
+    int count = 0;
+    if (cnt == 1) {
+      // the usual case: one candidate, its predecessors are compacted straight from the scan
+      const int j = cj[i * kCandCap];
+      const int thr = (cur[j] - score_q_any(plan, i, rdi, sm.kmer, k8, bins_seq, cls_stride, j)) - plan.thr_pred[i];
       for (int base = 0; base <= j; base += 32) {
         const int k = base + lane;
         const bool pred = (k <= j) && (prev[k] + Gq[j - k] >= thr);
         const unsigned bal = __ballot_sync(0xffffffffu, pred);
-        if (lane == 0 && bal) bitmap[base >> 5] |= bal;
+        if (pred) {
+          const int idx = count + __popc(bal & lt_mask);
+          if (idx < kCandCap) cj[(i - 1) * kCandCap + idx] = k;
+        }
+        count += __popc(bal);
       }
+    } else {
+      // several candidates: union of their predecessor sets through a bitmap (sorted and duplicate free)
+      for (int t = lane; t < words; t += 32) bitmap[t] = 0u;
       __syncwarp();
-    }
-    int count = 0;
-    for (int base = 0; base < P; base += 32) {
-      const unsigned word = bitmap[base >> 5];
-      const bool pred = (word >> lane) & 1u;
-      if (pred) {
-        const int idx = count + __popc(word & lt_mask);
-        if (idx < kCandCap) cj[(i - 1) * kCandCap + idx] = base + lane;
+      for (int c = 0; c < cnt; ++c) {
+        const int j = cj[i * kCandCap + c];
+        const int thr = (cur[j] - score_q_any(plan, i, rdi, sm.kmer, k8, bins_seq, cls_stride, j)) - plan.thr_pred[i];
+        for (int base = 0; base <= j; base += 32) {
+          const int k = base + lane;
+          const bool pred = (k <= j) && (prev[k] + Gq[j - k] >= thr);
+          const unsigned bal = __ballot_sync(0xffffffffu, pred);
+          if (lane == 0 && bal) bitmap[base >> 5] |= bal;
+        }
+        __syncwarp();
       }
-      count += __popc(word);
+      for (int base = 0; base < P; base += 32) {
+        const unsigned word = bitmap[base >> 5];
+        const bool pred = (word >> lane) & 1u;
+        if (pred) {
+          const int idx = count + __popc(word & lt_mask);
+          if (idx < kCandCap) cj[(i - 1) * kCandCap + idx] = base + lane;
+        }
+        count += __popc(word);
+      }
     }
     if (count > kCandCap) return false;
     if (lane == 0) cn[i - 1] = count;
     __syncwarp();
   }
-  // (3) exact forward evaluation on the candidate sets (lane = one candidate of the stage)
-  if (lane < cn[0]) {
-    const double r0 = score_exact_any(sm.rec[0], sm.pool, w, bins_seq, cls_stride, cj[lane]);
-    cv[lane] = r0;
-    cr[lane] = r0;
+  // (3) exact scores of all candidate cells (independent of the chain: one pass, lane = one candidate), then the
+  //     exact forward recurrence on the candidate sets
+  {
+    int tot = 0;
+    for (int i = 0; i < n; ++i) tot += cn[i];
+    if (tot <= 32) {
+      int st = -1, idx = 0, acc = 0;
+      for (int i = 0; i < n; ++i) {
+        if (st < 0 && lane < acc + cn[i]) {
+          st = i;
+          idx = lane - acc;
+        }
+        acc += cn[i];
+      }
+      if (st >= 0) cr[st * kCandCap + idx] = score_exact_any(sm.rec[st], sm.pool, w, bins_seq, cls_stride, cj[st * kCandCap + idx]);
+    } else {
+      for (int i = 0; i < n; ++i)
+        if (lane < cn[i]) cr[i * kCandCap + lane] = score_exact_any(sm.rec[i], sm.pool, w, bins_seq, cls_stride, cj[i * kCandCap + lane]);
+    }
   }
+  __syncwarp();
+  if (lane < cn[0]) cv[lane] = cr[lane];
   __syncwarp();
   for (int i = 1; i < n; ++i) {
     if (lane < cn[i]) {
       const int j = cj[i * kCandCap + lane];
-      const RecDesc rd = sm.rec[i];
-      const double rj = score_exact_any(rd, sm.pool, w, bins_seq, cls_stride, j);
+      const double rj = cr[i * kCandCap + lane];
       const ConView cvw = connector_view(p, v, i - 1);
       double best = neg_inf();
       int arg = -1;
@@ -430,7 +468,6 @@ __device__ bool refine_pair(const FastParams &f, const OrgView &v, const FastSme
         }
       }
       cv[i * kCandCap + lane] = best;
-      cr[i * kCandCap + lane] = rj;
       ca[i * kCandCap + lane] = arg;
     }
     __syncwarp();
@@ -486,6 +523,7 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
   int *rowsq = sm.rowsq + (size_t)slot * f.slotq_stride;
   int *rowsg = f.scratch + ((size_t)blockIdx.x * nwarps * NT + slot) * f.scratch_slot_stride;
   unsigned *w = sm.seqw + (size_t)slot * f.seqw_stride;
+  unsigned char *k8 = sm.k8 + (size_t)slot * f.k8_stride;
   const int nwords = (p.S + 15) >> 4;
 
   const int first = chunk * p.seqs_per_cta;
@@ -502,13 +540,15 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
       const unsigned *pw = p.packed + p.word_off[seq];
       for (int t = tl; t < f.seqw_stride; t += TEAM) w[t] = (t < nwords) ? __ldg(pw + t) : 0u;
       __syncwarp();
+      for (int q = tl; q < f.k8_stride; q += TEAM) k8[q] = (unsigned char)kmer_code(w, q);
+      __syncwarp();
       const unsigned char *bins_seq = p.bins + (size_t)seq * p.bins_row_stride;
       const size_t cls_stride = (size_t)p.n_seq_total * p.bins_row_stride;
       {
         const RecDesc rd0 = sm.rec[0];
         const bool spill = 0 <= n - 3;
         for (int j = tl; j < P + J; j += TEAM) {
-          int x = (j < P) ? score_q_any(plan, 0, rd0, sm.kmer, w, bins_seq, cls_stride, j) : 0;
+          int x = (j < P) ? score_q_any(plan, 0, rd0, sm.kmer, k8, bins_seq, cls_stride, j) : 0;
           if (x == kNanBinMarker) {
             nan_hit = true;
             x = 0;
@@ -528,7 +568,7 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
         const bool spill = i <= n - 3;
         int *gl = rowsg + (size_t)i * f.rowq_stride;
         for (int j = tl; j < P + J; j += TEAM) {
-          int r = (j < P) ? score_q_any(plan, i, rdi, sm.kmer, w, bins_seq, cls_stride, j) : 0;
+          int r = (j < P) ? score_q_any(plan, i, rdi, sm.kmer, k8, bins_seq, cls_stride, j) : 0;
           if (r == kNanBinMarker) {
             nan_hit = true;
             r = 0;
@@ -556,7 +596,7 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
         const int t_slot = warp * NT + t;
         done = refine_pair(f, v, sm, sm.rowsq + (size_t)t_slot * f.slotq_stride,
                            f.scratch + ((size_t)blockIdx.x * nwarps * NT + t_slot) * f.scratch_slot_stride,
-                           sm.seqw + (size_t)t_slot * f.seqw_stride, t_seq, warp, lane);
+                           sm.seqw + (size_t)t_slot * f.seqw_stride, sm.k8 + (size_t)t_slot * f.k8_stride, t_seq, warp, lane);
       }
       if (!done && lane == 0) {
         const int idx = atomicAdd(f.fb_count, 1);

@@ -84,6 +84,8 @@ class PackedPopulation:
     variants: dict = field(default_factory=dict)
     n_base_con: int = 0
     uploaded_con_size: int = -1
+    _con_org: np.ndarray = None
+    _con_mu_pos: np.ndarray = None
 
     @property
     def n_rec(self) -> np.ndarray:
@@ -102,13 +104,21 @@ class PackedPopulation:
         lengths = [int(x) for x in lengths]
         out = np.empty((len(lengths), self.n_org), dtype=np.int64)
         n_rec = self.n_rec
-        multi = np.nonzero(n_rec > 1)[0]
         threshold = np.log(1E-15)
         extra = []
         extra_off = self.con_pool.size
+        if self._con_org is None:
+            # per-connector views for the vectorised trigger test: owner organism, position of mu in con_pool
+            nc = np.maximum(n_rec - 1, 0)
+            self._con_org = np.repeat(np.arange(self.n_org), nc)
+            first = np.cumsum(nc) - nc
+            within = np.arange(int(nc.sum())) - np.repeat(first, nc)
+            self._con_mu_pos = self.con_base[self._con_org] + within * (2 * self.con_M[self._con_org].astype(np.int64) + 2)
+        mu_all = self.con_pool[self._con_mu_pos] if self._con_mu_pos.size else np.zeros(0)
         for ci, S in enumerate(lengths):
             out[ci, :] = self.con_base
-            for o in multi:
+            hot = np.unique(self._con_org[float(S) + 0.5 < mu_all]) if mu_all.size else ()
+            for o in hot:
                 key = (int(o), S)
                 if key in self.variants:
                     out[ci, o] = self.variants[key]
@@ -120,9 +130,6 @@ class PackedPopulation:
                 idx = S - int(self.sum_len[o])
                 if idx < 0 or idx >= M:
                     continue  # inadmissible pair; the library reports it
-                mus = self.con_pool[base:base + nc * stride:stride]
-                if not np.any(float(S) + 0.5 < mus):
-                    continue
                 block = None
                 for c in range(nc):
                     mu = float(self.con_pool[base + c * stride])
@@ -140,6 +147,12 @@ class PackedPopulation:
         if extra:
             self.con_pool = np.concatenate([self.con_pool] + extra)
         return out
+
+
+def _f64(a) -> np.ndarray:
+    if isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous:
+        return a
+    return np.ascontiguousarray(a, dtype=np.float64)
 
 
 def pack_population(organisms) -> PackedPopulation:
@@ -161,18 +174,36 @@ def pack_population(organisms) -> PackedPopulation:
         n = len(rtypes)
         if n < 1:
             raise ValueError(f"organism {getattr(org, '_id', o)} has no recognizers")
-        rlens = np.asarray(org.recognizer_lengths, dtype=np.int32)
-        if rlens.size != n:
+        rlens = org.recognizer_lengths
+        rl = rlens.tolist() if isinstance(rlens, np.ndarray) else [int(x) for x in rlens]
+        if len(rl) != n:
             raise ValueError("organism is not flattened: recognizer_lengths does not match recognizer_types")
-        pssm = np.ascontiguousarray(org.recognizers_flat, dtype=np.float64)
-        models = np.ascontiguousarray(org.recognizer_models, dtype=np.float64)
-        edges = np.ascontiguousarray(org.recognizer_bin_edges, dtype=np.float64)
-        bin_nums = np.asarray(org.recognizer_bin_nums, dtype=np.int32)
+        total_len = sum(rl)
+        pssm = _f64(org.recognizers_flat)
+        all_pssm = rtypes == 'p' * n
+        if not all_pssm:
+            models = _f64(org.recognizer_models)
+            edges = _f64(org.recognizer_bin_edges)
+            bin_nums = np.asarray(org.recognizer_bin_nums, dtype=np.int32)
         m_off = a_off = e_off = shape_i = 0
         org_parts = []
         org_pool = 0
-        for i, t in enumerate(rtypes):
-            L = int(rlens[i])
+        if all_pssm:
+            # common case, no per-recognizer python work: the PSSMs are already back to back in recognizers_flat
+            if pssm.size != 4 * total_len:
+                raise ValueError("recognizers_flat does not match the PSSM lengths")
+            at = pool_off
+            for L in rl:
+                datas.append(at)
+                at += 4 * L
+            types.extend([112] * n)
+            lens.extend(rl)
+            nbs.extend([0] * n)
+            class_of.extend([-1] * n)
+            org_parts.append(pssm)
+            org_pool = 4 * total_len
+        for i, t in enumerate(rtypes if not all_pssm else ()):
+            L = rl[i]
             datas.append(pool_off + org_pool)
             if t in "pP":
                 org_parts.append(pssm[m_off:m_off + 4 * L])
@@ -208,8 +239,8 @@ def pack_population(organisms) -> PackedPopulation:
         pool_off += org_pool
         rec_begin[o + 1] = rec_begin[o] + n
         pool_begin[o + 1] = pool_off
-        sum_len[o] = int(rlens.sum())
-        con = np.ascontiguousarray(org.connectors_scores_flat, dtype=np.float64)
+        sum_len[o] = total_len
+        con = _f64(org.connectors_scores_flat)
         con_base[o] = con_off
         if n > 1:
             if con.size == 2 * (n - 1):
