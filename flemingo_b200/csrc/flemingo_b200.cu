@@ -369,7 +369,7 @@ static int upload_population(fl_ctx *ctx, Population &P, const fl_population *po
       if (!is_p && !is_s) return fail(FL_E_ARG, "organism %d recognizer %d: unknown type '%c'", o, i, t);
       if (L < 1 || (is_s && L < 5)) return fail(FL_E_ARG, "organism %d recognizer %d: length %d not allowed for type '%c'", o, i, L, t);
       if (is_s && pop->rec_nb[rb + i] < 2) return fail(FL_E_ARG, "organism %d recognizer %d: shape model needs >= 2 bin edges", o, i);
-      const long long need = is_p ? 4LL * L : 3LL * pop->rec_nb[rb + i] - 2;
+      const long long need = is_p ? 4LL * L : 2LL * pop->rec_nb[rb + i] - 2;
       const long long off = pop->rec_data[rb + i];
       if (off < pop->pool_begin[o] || off + need > pop->pool_begin[o + 1]) return fail(FL_E_ARG, "organism %d recognizer %d: data outside the organism's pool slice", o, i);
       sl += L;
@@ -839,7 +839,6 @@ extern "C" int fl_calculate(fl_ctx *ctx, const char *sequence, int seq_len, cons
       if (nb < 2) return fail(FL_E_ARG, "fl_calculate: shape recognizer %d has %d bin edges", i, nb);
       rec_nb[i] = nb;
       pool.insert(pool.end(), bin_freqs + a_off, bin_freqs + a_off + 2LL * (nb - 1));  // null ++ alt (organism.c:159-172)
-      pool.insert(pool.end(), bin_edges + e_off, bin_edges + e_off + nb);
       rec_class[i] = (int)cls_kind.size();
       cls_kind.push_back(rec_types[i]);
       cls_len.push_back(L);

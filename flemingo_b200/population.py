@@ -155,119 +155,133 @@ def _f64(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+def _segment_exclusive_cumsum(values: np.ndarray, seg_first: np.ndarray, seg_id: np.ndarray) -> np.ndarray:
+    """Exclusive prefix sum of `values` restarting at every segment (seg_first[s] = first index of segment s)."""
+    if values.size == 0:
+        return values.astype(np.int64)
+    csum = np.cumsum(values, dtype=np.int64) - values
+    return csum - csum[seg_first][seg_id]
+
+
 def pack_population(organisms) -> PackedPopulation:
-    """Packs organisms (flattened, see module docstring) into one PackedPopulation."""
+    """Packs organisms (flattened, see module docstring) into one PackedPopulation.
+
+    Vectorised: a handful of list comprehensions and numpy concatenations, no per-recognizer Python work.
+    Pool layout per organism: recognizers_flat (all its PSSMs, [col][A,G,C,T]) followed by recognizer_models
+    (null[nb-1] ++ alt[nb-1] per shape recognizer, organism.c:159-172).  Bin edges live in the shape classes.
+    """
     n_org = len(organisms)
+    type_strs = [org.recognizer_types for org in organisms]
+    n_rec = np.fromiter((len(t) for t in type_strs), dtype=np.int64, count=n_org)
+    if n_org and int(n_rec.min()) < 1:
+        bad = int(np.argmin(n_rec))
+        raise ValueError(f"organism {getattr(organisms[bad], '_id', bad)} has no recognizers")
     rec_begin = np.zeros(n_org + 1, dtype=np.int32)
+    np.cumsum(n_rec, out=rec_begin[1:])
+    n_total = int(rec_begin[-1])
+    rec_type = np.frombuffer("".join(type_strs).encode("ascii"), dtype=np.uint8) if n_total else np.zeros(0, np.uint8)
+    len_parts = [org.recognizer_lengths for org in organisms]
+    rec_len = np.concatenate(len_parts).astype(np.int32, copy=False) if n_org else np.zeros(0, np.int32)
+    if rec_len.size != n_total:
+        raise ValueError("an organism is not flattened: recognizer_lengths does not match recognizer_types")
+    is_p = (rec_type == 112) | (rec_type == 80)
+    org_of = np.repeat(np.arange(n_org), n_rec)
+    seg_first = rec_begin[:-1].astype(np.int64)
+
+    pssm_parts = [_f64(org.recognizers_flat) for org in organisms]
+    pssm_sizes = np.fromiter((a.size for a in pssm_parts), dtype=np.int64, count=n_org)
+    size_p = np.where(is_p, 4 * rec_len.astype(np.int64), 0)
+    if not np.array_equal(np.bincount(org_of, weights=size_p, minlength=n_org).astype(np.int64), pssm_sizes):
+        raise ValueError("recognizers_flat does not match the PSSM lengths of an organism")
+    any_shape = not bool(is_p.all())
+    rec_nb = np.zeros(n_total, dtype=np.int32)
+    rec_class = np.full(n_total, -1, dtype=np.int32)
+    cls_kind = np.zeros(0, np.uint8)
+    cls_len = np.zeros(0, np.int32)
+    cls_nb = np.zeros(0, np.int32)
+    cls_edges = np.zeros(0, np.int64)
+    edges_pool = np.zeros(0, np.float64)
+    if any_shape:
+        model_parts = [_f64(org.recognizer_models) for org in organisms]
+        model_sizes = np.fromiter((a.size for a in model_parts), dtype=np.int64, count=n_org)
+        nb_shapes = np.concatenate([np.asarray(org.recognizer_bin_nums, dtype=np.int32) for org in organisms])
+        shape_idx = np.nonzero(~is_p)[0]
+        if nb_shapes.size != shape_idx.size:
+            raise ValueError("recognizer_bin_nums does not match the number of shape recognizers")
+        rec_nb[shape_idx] = nb_shapes
+        size_m = np.where(is_p, 0, 2 * (rec_nb.astype(np.int64) - 1))
+        if not np.array_equal(np.bincount(org_of, weights=size_m, minlength=n_org).astype(np.int64), model_sizes):
+            raise ValueError("recognizer_models does not match the shape recognizers of an organism")
+        pool_parts = [x for pair in zip(pssm_parts, model_parts) for x in pair]
+        org_pool = pssm_sizes + model_sizes
+        # shape classes: distinct (kind, length, edges) -- grouped by the number of edges so rows can be compared
+        all_edges = np.concatenate([_f64(org.recognizer_bin_edges) for org in organisms])
+        if all_edges.size != int(nb_shapes.sum()):
+            raise ValueError("recognizer_bin_edges does not match recognizer_bin_nums")
+        e_start = np.cumsum(nb_shapes, dtype=np.int64) - nb_shapes
+        kinds = rec_type[shape_idx] | 32   # lower case
+        lens_s = rec_len[shape_idx]
+        ck, cl, cn, ce, pools = [], [], [], [], []
+        e_off = 0
+        for nb in np.unique(nb_shapes):
+            sel = np.nonzero(nb_shapes == nb)[0]
+            rows = all_edges[(e_start[sel][:, None] + np.arange(nb)[None, :])]
+            key = np.concatenate([kinds[sel][:, None].astype(np.float64), lens_s[sel][:, None].astype(np.float64), rows], axis=1)
+            # NaN-free keys: np.unique on the byte view keeps bit patterns distinct
+            view = np.ascontiguousarray(key).view(np.dtype((np.void, key.dtype.itemsize * key.shape[1]))).ravel()
+            _, first, inverse = np.unique(view, return_index=True, return_inverse=True)
+            rec_class[shape_idx[sel]] = len(ck) + inverse.ravel()
+            for f in first:
+                ck.append(int(kinds[sel][f]))
+                cl.append(int(lens_s[sel][f]))
+                cn.append(int(nb))
+                ce.append(e_off)
+                pools.append(rows[f])
+                e_off += int(nb)
+        cls_kind = np.asarray(ck, dtype=np.uint8)
+        cls_len = np.asarray(cl, dtype=np.int32)
+        cls_nb = np.asarray(cn, dtype=np.int32)
+        cls_edges = np.asarray(ce, dtype=np.int64)
+        edges_pool = np.ascontiguousarray(np.concatenate(pools), dtype=np.float64)
+    else:
+        size_m = np.zeros(n_total, dtype=np.int64)
+        pool_parts = pssm_parts
+        org_pool = pssm_sizes
     pool_begin = np.zeros(n_org + 1, dtype=np.int64)
-    con_base = np.zeros(n_org, dtype=np.int64)
+    np.cumsum(org_pool, out=pool_begin[1:])
+    rec_pool = np.concatenate(pool_parts) if n_org else np.zeros(0)
+    # recognizer data offsets: PSSMs in order inside the organism's PSSM segment, shape models in order inside its model segment
+    off_p = _segment_exclusive_cumsum(size_p, seg_first, org_of)
+    off_m = _segment_exclusive_cumsum(size_m, seg_first, org_of)
+    rec_data = pool_begin[:-1][org_of] + np.where(is_p, off_p, pssm_sizes[org_of] + off_m)
+
+    sum_len = np.bincount(org_of, weights=rec_len, minlength=n_org).astype(np.int32) if n_total else np.zeros(n_org, np.int32)
+    con_parts = [_f64(org.connectors_scores_flat) for org in organisms]
+    con_sizes = np.fromiter((a.size for a in con_parts), dtype=np.int64, count=n_org)
+    multi = n_rec > 1
+    if bool(np.any(multi & (con_sizes == 2 * (n_rec - 1)))):
+        raise NotImplementedError(
+            "organism.PRECOMPUTE=false (connectors without pdf/cdf tables) uses the reference's legacy "
+            "float maths (connector.c:70-72, _aux.c:47-139); the GPU path requires precomputed tables")
     con_M = np.zeros(n_org, dtype=np.int32)
-    sum_len = np.zeros(n_org, dtype=np.int32)
     pcs = np.zeros(n_org, dtype=np.float64)
-    types, lens, nbs, datas, pool_parts, con_parts, ids = [], [], [], [], [], [], []
-    classes, class_of, cls_kind, cls_len, cls_nb, cls_edges, edge_parts = {}, [], [], [], [], [], []
-    edge_off = 0
-    pool_off = 0
-    con_off = 0
-    for o, org in enumerate(organisms):
-        rtypes = org.recognizer_types
-        n = len(rtypes)
-        if n < 1:
-            raise ValueError(f"organism {getattr(org, '_id', o)} has no recognizers")
-        rlens = org.recognizer_lengths
-        rl = rlens.tolist() if isinstance(rlens, np.ndarray) else [int(x) for x in rlens]
-        if len(rl) != n:
-            raise ValueError("organism is not flattened: recognizer_lengths does not match recognizer_types")
-        total_len = sum(rl)
-        pssm = _f64(org.recognizers_flat)
-        all_pssm = rtypes == 'p' * n
-        if not all_pssm:
-            models = _f64(org.recognizer_models)
-            edges = _f64(org.recognizer_bin_edges)
-            bin_nums = np.asarray(org.recognizer_bin_nums, dtype=np.int32)
-        m_off = a_off = e_off = shape_i = 0
-        org_parts = []
-        org_pool = 0
-        if all_pssm:
-            # common case, no per-recognizer python work: the PSSMs are already back to back in recognizers_flat
-            if pssm.size != 4 * total_len:
-                raise ValueError("recognizers_flat does not match the PSSM lengths")
-            at = pool_off
-            for L in rl:
-                datas.append(at)
-                at += 4 * L
-            types.extend([112] * n)
-            lens.extend(rl)
-            nbs.extend([0] * n)
-            class_of.extend([-1] * n)
-            org_parts.append(pssm)
-            org_pool = 4 * total_len
-        for i, t in enumerate(rtypes if not all_pssm else ()):
-            L = rl[i]
-            datas.append(pool_off + org_pool)
-            if t in "pP":
-                org_parts.append(pssm[m_off:m_off + 4 * L])
-                if org_parts[-1].size != 4 * L:
-                    raise ValueError("recognizers_flat is shorter than the PSSM lengths require")
-                m_off += 4 * L
-                org_pool += 4 * L
-                nbs.append(0)
-                class_of.append(-1)
-            else:
-                nb = int(bin_nums[shape_i])
-                # parse_org (organism.c:159-185): null = models+a, alt = models+a+(nb-1), edges = edges+e
-                org_parts.append(models[a_off:a_off + 2 * (nb - 1)])
-                org_parts.append(edges[e_off:e_off + nb])
-                key = (t.lower(), L, edges[e_off:e_off + nb].tobytes())
-                if key not in classes:
-                    classes[key] = len(classes)
-                    cls_kind.append(ord(t))
-                    cls_len.append(L)
-                    cls_nb.append(nb)
-                    cls_edges.append(edge_off)
-                    edge_parts.append(edges[e_off:e_off + nb])
-                    edge_off += nb
-                class_of.append(classes[key])
-                a_off += 2 * (nb - 1)
-                e_off += nb
-                org_pool += 3 * nb - 2
-                shape_i += 1
-                nbs.append(nb)
-            types.append(ord(t))
-            lens.append(L)
-        pool_parts.extend(org_parts)
-        pool_off += org_pool
-        rec_begin[o + 1] = rec_begin[o] + n
-        pool_begin[o + 1] = pool_off
-        sum_len[o] = total_len
-        con = _f64(org.connectors_scores_flat)
-        con_base[o] = con_off
-        if n > 1:
-            if con.size == 2 * (n - 1):
-                raise NotImplementedError(
-                    "organism.PRECOMPUTE=false (connectors without pdf/cdf tables) uses the reference's legacy "
-                    "float maths (connector.c:70-72, _aux.c:47-139); the GPU path requires precomputed tables")
-            M = int(org.connectors[0].max_seq_length)
-            if con.size != (n - 1) * (2 * M + 2):
-                raise ValueError("connectors_scores_flat does not match (n-1) * (2*max_seq_length + 2)")
-            con_M[o] = M
-            pcs[o] = float(org.connectors[0].pseudo_count)
-            con_parts.append(con)
-            con_off += con.size
-        ids.append(getattr(org, "_id", str(o)))
-    rec_pool = np.concatenate(pool_parts) if pool_parts else np.zeros(0)
-    con_pool = np.concatenate(con_parts) if con_parts else np.zeros(0)
+    for o in np.nonzero(multi)[0]:
+        first = organisms[o].connectors[0]
+        con_M[o] = first.max_seq_length
+        pcs[o] = first.pseudo_count
+    if bool(np.any(multi & (con_sizes != (n_rec - 1) * (2 * con_M.astype(np.int64) + 2)))):
+        raise ValueError("connectors_scores_flat does not match (n-1) * (2*max_seq_length + 2)")
+    con_sizes = np.where(multi, con_sizes, 0)
+    con_base = np.cumsum(con_sizes) - con_sizes
+    con_pool = np.concatenate([c for c, m in zip(con_parts, multi) if m]) if bool(multi.any()) else np.zeros(0)
     return PackedPopulation(
-        n_org=n_org, rec_begin=rec_begin, rec_type=np.asarray(types, dtype=np.uint8),
-        rec_len=np.asarray(lens, dtype=np.int32), rec_nb=np.asarray(nbs, dtype=np.int32),
-        rec_data=np.asarray(datas, dtype=np.int64), pool_begin=pool_begin,
+        n_org=n_org, rec_begin=rec_begin, rec_type=np.ascontiguousarray(rec_type), rec_len=np.ascontiguousarray(rec_len),
+        rec_nb=rec_nb, rec_data=np.ascontiguousarray(rec_data, dtype=np.int64), pool_begin=pool_begin,
         rec_pool=np.ascontiguousarray(rec_pool, dtype=np.float64), con_M=con_M,
-        con_pool=np.ascontiguousarray(con_pool, dtype=np.float64), con_base=con_base, sum_len=sum_len,
-        pseudo_count=pcs, ids=ids, n_base_con=int(con_pool.size),
-        rec_class=np.asarray(class_of, dtype=np.int32), cls_kind=np.asarray(cls_kind, dtype=np.uint8),
-        cls_len=np.asarray(cls_len, dtype=np.int32), cls_nb=np.asarray(cls_nb, dtype=np.int32),
-        cls_edges=np.asarray(cls_edges, dtype=np.int64),
-        edges_pool=np.ascontiguousarray(np.concatenate(edge_parts) if edge_parts else np.zeros(0), dtype=np.float64))
+        con_pool=np.ascontiguousarray(con_pool, dtype=np.float64), con_base=con_base.astype(np.int64), sum_len=sum_len,
+        pseudo_count=pcs, ids=[getattr(org, "_id", str(i)) for i, org in enumerate(organisms)],
+        n_base_con=int(con_pool.size), rec_class=rec_class, cls_kind=cls_kind, cls_len=cls_len, cls_nb=cls_nb,
+        cls_edges=cls_edges, edges_pool=edges_pool)
 
 
 def placement_cost(packed: PackedPopulation, seq_len: int) -> np.ndarray:

@@ -62,7 +62,7 @@ typedef struct fl_population {
   const int *rec_nb;           /* [n_rec_total] number of bin EDGES of a shape recognizer (0 for 'p') */
   const long long *rec_data;   /* [n_rec_total] offset into rec_pool: PSSM = 4*len doubles, column major
                                   [col][A,G,C,T] (organism_object.py:1455-1458); shape = null[nb-1] ++
-                                  alt[nb-1] ++ edges[nb] (organism.c:159-185) */
+                                  alt[nb-1] (organism.c:159-172); the bin edges live in the shape classes */
   const long long *pool_begin; /* [n_org+1] slice of rec_pool used by organism o */
   const double *rec_pool;
   long long n_pool;

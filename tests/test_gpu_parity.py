@@ -206,3 +206,86 @@ def test_single_recognizer_and_tight_fits(engine):
         E, G, R, Cs = oracle.place_all([org], seqs, "restated")
         assert np.array_equal(res.energies, E) and np.array_equal(res.gaps, G)
         assert np.array_equal(res.rec_scores, R) and np.array_equal(res.con_scores, Cs)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the integer filter pass: every tile configuration, its hand-back paths, and its fixed-point range
+# ---------------------------------------------------------------------------------------------------------------
+def _assert_equals_oracle(engine, orgs, seqs):
+    engine.upload_population(orgs)
+    res = engine.place(engine.upload_sequences(seqs, 0), trace=True)
+    E, G, R, Cs = oracle.place_all(orgs, seqs, "restated")
+    assert np.array_equal(res.energies, E)
+    assert np.array_equal(res.gaps, G)
+    assert np.array_equal(res.rec_scores, R)
+    assert np.array_equal(res.con_scores, Cs)
+    return res
+
+
+@pytest.mark.parametrize("S", [24, 40, 66, 97, 130, 175, 210, 260, 300, 340, 450, 700, 1100])
+def test_every_tile_configuration_vs_oracle(engine, S):
+    """Sequence lengths chosen so that P = S - sum(L) + 1 walks through the (J, TEAM) table of the fast path and
+    the tile sizes of the exact kernel, including multi-round folds."""
+    from flemingo_b200 import synthetic
+    n_org = 10 if S <= 450 else 4
+    orgs = synthetic.mixed_organisms(n_org, S, 100 + S, max_rec=4) + synthetic.pssm_organisms(4, S, 200 + S, n_rec=2, rec_len=6)
+    orgs = [o for o in orgs if o.sum_recognizer_lengths <= S - 3]
+    seqs = synthetic.random_sequences(9 if S <= 450 else 3, S, S) + synthetic.random_sequences(2, S - 3, S + 1)
+    _assert_equals_oracle(engine, orgs, seqs)
+
+
+def test_massive_ties_are_handed_to_the_exact_kernel(engine):
+    """Homopolymers and short repeats make every placement tie: the candidate sets overflow, the pairs go to the
+    list-mode exact kernel, and the reference's first-k / first-j tie rule still decides the offsets."""
+    from flemingo_b200 import synthetic
+    orgs = synthetic.pssm_organisms(6, 200, 31, n_rec=3, rec_len=7)
+    seqs = ["a" * 200, "c" * 200, "ac" * 100, "acg" * 66 + "ac", "t" * 100 + "g" * 100] + synthetic.random_sequences(3, 200, 32)
+    engine.path_stats()
+    _assert_equals_oracle(engine, orgs, seqs)
+    fast, handed_back = engine.path_stats()
+    if not engine.exact_only:
+        assert fast == len(orgs) * len(seqs)
+        assert handed_back >= len(orgs) * 2               # at least the homopolymers
+        assert handed_back < fast                         # the random sequences stay on the integer path
+
+
+def test_unknown_bytes_take_the_exact_path(engine):
+    from flemingo_b200 import synthetic
+    orgs = synthetic.mixed_organisms(8, 120, 41, max_rec=4)
+    rng = np.random.default_rng(5)
+    seqs = ["".join(rng.choice(list("acgtnNx-ACGT"), 120)) for _ in range(5)] + synthetic.random_sequences(4, 120, 42)
+    engine.path_stats()
+    _assert_equals_oracle(engine, orgs, seqs)
+    fast, handed_back = engine.path_stats()
+    if not engine.exact_only and fast:
+        assert handed_back >= 5 * sum(1 for o in orgs if len(o.recognizer_types) >= 2)
+
+
+def test_extreme_pssm_values_shrink_the_fixed_point_scale_but_stay_exact(engine):
+    """PWM columns with zero probabilities give PSSM entries of log2(1e-10) = -33.22: the value range grows, the
+    fixed-point scale shrinks, thresholds widen -- results must not change."""
+    from flemingo_b200 import objects, synthetic
+    rng = np.random.default_rng(77)
+    orgs = []
+    for o in range(6):
+        recs = []
+        for _ in range(3):
+            cols = []
+            for _ in range(int(rng.integers(4, 11))):
+                p = rng.dirichlet([0.3] * 4)
+                p[rng.integers(0, 4)] = 0.0
+                p = p / p.sum()
+                cols.append({"a": float(p[0]), "g": float(p[1]), "c": float(p[2]), "t": float(p[3])})
+            recs.append(objects.PssmObject(np.array(cols), synthetic.CONF_PSSM))
+        cons = [synthetic.random_connector(rng, 150) for _ in range(2)]
+        orgs.append(synthetic.assemble(f"x{o}", recs, cons))
+    _assert_equals_oracle(engine, orgs, synthetic.random_sequences(12, 150, 78))
+
+
+def test_full_size_config3_sample_vs_oracle(engine):
+    """BASELINE config 3 shapes (mixed PSSM + shape organisms, up to 6 recognizers, 300 bp): a slice big enough to
+    fill several CTAs per bucket, every pair against the oracle."""
+    from flemingo_b200 import synthetic
+    orgs = synthetic.mixed_organisms(120, 300, 3)
+    seqs = synthetic.random_sequences(40, 300, 1)
+    _assert_equals_oracle(engine, orgs, seqs)
