@@ -13,6 +13,7 @@ ranks every rank owns 256 organisms (weak scaling), sequences replicated, one al
   e2e    wall-clocked through the public host API (set_population_fitness on Python organisms and str
          sequences): host packing, H2D of population + sequences, kernels, D2H of the statistics
   roofline       ALU line of SURVEY.md section 8d (3 flop-equivalents per DP cell vs SMs x 128 lanes x max clock);
+  roofline_dpx   DP cells per second vs the measured DPX (VIADDMNMX) cell rate of tools/microbench.cu
   roofline_hbm   the HBM line (algorithmic bytes vs measured copy bandwidth) showing the path is not memory bound
   cpu_baseline   the unmodified reference C extension (oracle/_ref) on the host cores, bounded sample
 """
@@ -35,6 +36,15 @@ sys.path.insert(0, str(ROOT))
 METRIC = "organism x sequence placements/sec"
 UNIT = "placements/s"
 SM_COUNT, LANES_PER_SM = 148, 128
+DPX_PEAK_TCELLS = 18.4   # measured on this pool's B200: one VIADDMNMX per cell, 64 lanes/clk/SM (tools/microbench.cu)
+
+
+def load_traffic(workload: str):
+    """dram__bytes_read + dram__bytes_write of one launch of the dominant kernel, from the committed ncu capture."""
+    p = ROOT / "profiles" / "traffic.json"
+    if p.exists():
+        return json.loads(p.read_text()).get(workload)
+    return None
 
 
 def load_peaks():
@@ -85,7 +95,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
@@ -283,12 +293,15 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         value = placements / (ms_per_step * 1e-3)
         cells, adds = cells_per_placement(orgs, w["seq_len"])
         hbm_peak, sm_max_mhz, how = load_peaks()
-        # dominant kernel = place_tiled_kernel (two launches per step, one per sequence set), per GPU
+        # dominant kernel = place_fast_kernel (the integer DPX filter pass + exact refinement; one launch per
+        # sequence set and tile bucket, two per step here), per GPU
         k_ms = place_ms / args.steps / 2
         k_pairs = n_local * n_seq / 2
         flops = k_pairs * (3.0 * cells + adds)
         alu_peak = SM_COUNT * LANES_PER_SM * sm_max_mhz * 1e6 / 1e12
         achieved = flops / (k_ms * 1e-3) / 1e12
+        cells_per_s = k_pairs * cells / (k_ms * 1e-3)
+        traffic = load_traffic(args.workload)
         bytes_alg = k_pairs * ((w["seq_len"] + 3) // 4 + 8)
         hbm_achieved = bytes_alg / (k_ms * 1e-3) / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -297,11 +310,14 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 "e2e": {"value": placements / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s * 1e3},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "alu", "kernel": "place_tiled_kernel", "achieved": achieved, "peak": alu_peak,
+                "roofline": {"bound": "alu", "kernel": "place_fast_kernel", "achieved": achieved, "peak": alu_peak,
                              "unit": "TFLOP/s (non-tensor flop-equivalents: 3 per DP cell + 1 per score add)",
-                             "frac": achieved / alu_peak, "traffic": None,
+                             "frac": achieved / alu_peak, "traffic": traffic,
                              "peak_source": f"{SM_COUNT} SMs x {LANES_PER_SM} lanes x {sm_max_mhz:.0f} MHz ({how} max SM clock)",
-                             "cells_per_s": k_pairs * cells / (k_ms * 1e-3), "kernel_ms": k_ms},
+                             "cells_per_s": cells_per_s, "kernel_ms": k_ms},
+                "roofline_dpx": {"bound": "alu-dpx", "achieved": cells_per_s / 1e12, "peak": DPX_PEAK_TCELLS, "unit": "Tcell/s",
+                                 "frac": cells_per_s / 1e12 / DPX_PEAK_TCELLS,
+                                 "peak_source": "measured: int32 VIADDMNMX cell rate, profiles/r1_microbench_pipe_rates.txt"},
                 "roofline_hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": hbm_achieved / hbm_peak, "traffic": None, "peak_source": how},
                 "wall_ms_per_step": wall_ms / args.steps}
