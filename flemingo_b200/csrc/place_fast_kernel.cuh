@@ -499,6 +499,60 @@ __device__ bool refine_pair(const FastParams &f, const OrgView &v, const FastSme
   return true;
 }
 
+// Adds the quantised scores of recognizer r to a row (or, for stage 0, writes them): row[j] (+)= Rq_r[j], j < P,
+// zeroes the J padding entries behind the row, and mirrors the finished row to global scratch when a later
+// refinement needs it.  The recognizer kind and the number of 4-mer groups are hoisted out of the offset loop.
+template <int NG, int TEAM, bool FIRST>
+__device__ __forceinline__ void add_pssm_scores_q(const int *__restrict__ tab, int ng, const unsigned char *__restrict__ k,
+                                                  int *__restrict__ row, int *__restrict__ glob, int P, int tl) {
+#pragma unroll 4
+  for (int j = tl; j < P; j += TEAM) {
+    int v = FIRST ? 0 : row[j];
+    if (NG > 0) {
+#pragma unroll
+      for (int g = 0; g < NG; ++g) v += tab[256 * g + k[j + 4 * g]];
+    } else {
+      for (int g = 0; g < ng; ++g) v += tab[256 * g + k[j + 4 * g]];
+    }
+    row[j] = v;
+    if (glob) glob[j] = v;
+  }
+}
+
+template <int J, int TEAM, bool FIRST>
+__device__ __forceinline__ void add_scores_q(const FastPlan &plan, int r, const RecDesc &rd, const int *__restrict__ kmer,
+                                             const unsigned char *__restrict__ k8, const unsigned char *__restrict__ bins_seq,
+                                             size_t cls_stride, int *__restrict__ row, int *__restrict__ glob, int P, int tl,
+                                             bool &nan_hit) {
+  if (rd.kind == 0) {
+    const int *tab = kmer + plan.kmer_off[r];
+    const unsigned char *k = k8 + rd.fwd;
+    const int ng = plan.ngroups[r];
+    switch (ng) {
+      case 1: add_pssm_scores_q<1, TEAM, FIRST>(tab, ng, k, row, glob, P, tl); break;
+      case 2: add_pssm_scores_q<2, TEAM, FIRST>(tab, ng, k, row, glob, P, tl); break;
+      case 3: add_pssm_scores_q<3, TEAM, FIRST>(tab, ng, k, row, glob, P, tl); break;
+      case 4: add_pssm_scores_q<4, TEAM, FIRST>(tab, ng, k, row, glob, P, tl); break;
+      default: add_pssm_scores_q<0, TEAM, FIRST>(tab, ng, k, row, glob, P, tl); break;
+    }
+  } else {
+    const int *tab = kmer + plan.kmer_off[r];
+    const unsigned char *b = bins_seq + (size_t)rd.cls * cls_stride + rd.fwd;
+#pragma unroll 4
+    for (int j = tl; j < P; j += TEAM) {
+      int x = tab[b[j]];
+      if (x == kNanBinMarker) {
+        nan_hit = true;
+        x = 0;
+      }
+      const int v = FIRST ? x : row[j] + x;
+      row[j] = v;
+      if (glob) glob[j] = v;
+    }
+  }
+  for (int t = tl; t < J; t += TEAM) row[P + t] = 0;  // padding behind the row: 0 + sentinel cannot wrap
+}
+
 // ------------------------------------------------------------------------------------------------
 // The fast kernel.  CTA = one organism x a chunk of sequences; a warp holds 32/TEAM pairs at a time, each
 // placed by a team of TEAM lanes with J x J register tiles of DPX cells.
@@ -544,19 +598,8 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
       __syncwarp();
       const unsigned char *bins_seq = p.bins + (size_t)seq * p.bins_row_stride;
       const size_t cls_stride = (size_t)p.n_seq_total * p.bins_row_stride;
-      {
-        const RecDesc rd0 = sm.rec[0];
-        const bool spill = 0 <= n - 3;
-        for (int j = tl; j < P + J; j += TEAM) {
-          int x = (j < P) ? score_q_any(plan, 0, rd0, sm.kmer, k8, bins_seq, cls_stride, j) : 0;
-          if (x == kNanBinMarker) {
-            nan_hit = true;
-            x = 0;
-          }
-          rowsq[j] = x;
-          if (spill && j < P) rowsg[j] = x;
-        }
-      }
+      add_scores_q<J, TEAM, true>(plan, 0, sm.rec[0], sm.kmer, k8, bins_seq, cls_stride, rowsq, (0 <= n - 3) ? rowsg : nullptr, P, tl,
+                                  nan_hit);
       __syncwarp();
       for (int i = 1; i < n; ++i) {
         const int *prev = rowsq + (size_t)((i - 1) & 1) * f.rowq_stride;
@@ -564,19 +607,8 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
         const int *Gq = sm.Gq + (size_t)(i - 1) * f.gq_stride + kGPad;
         dp_stage<J, TEAM, OpI32>(prev, cur, Gq, P, tl, plan.sent);
         __syncwarp();
-        const RecDesc rdi = sm.rec[i];
-        const bool spill = i <= n - 3;
-        int *gl = rowsg + (size_t)i * f.rowq_stride;
-        for (int j = tl; j < P + J; j += TEAM) {
-          int r = (j < P) ? score_q_any(plan, i, rdi, sm.kmer, k8, bins_seq, cls_stride, j) : 0;
-          if (r == kNanBinMarker) {
-            nan_hit = true;
-            r = 0;
-          }
-          const int x = (j < P) ? cur[j] + r : 0;
-          cur[j] = x;
-          if (spill && j < P) gl[j] = x;
-        }
+        add_scores_q<J, TEAM, false>(plan, i, sm.rec[i], sm.kmer, k8, bins_seq, cls_stride, cur,
+                                     (i <= n - 3) ? rowsg + (size_t)i * f.rowq_stride : nullptr, P, tl, nan_hit);
         __syncwarp();
       }
     }
