@@ -191,7 +191,7 @@ def run_reference(args, rank: int, world: int):
 def bench_config(args, w, n_org_total):
     return {"workload": f"BASELINE config {args.workload[1:]} ({args.workload}): {n_org_total} organisms x "
                         f"({w['n_pos']} pos + {w['n_neg']} neg) sequences of {w['seq_len']} bp",
-            "organisms": n_org_total, "organisms_per_gpu": w["n_org"], "sequences": w["n_pos"] + w["n_neg"], "seq_len": w["seq_len"],
+            "organisms": n_org_total, "organisms_per_gpu": n_org_total // max(1, args.gpus), "sequences": w["n_pos"] + w["n_neg"], "seq_len": w["seq_len"],
             "fitness": "Welch", "offsets": False, "parallelism": f"organism-sharded x{max(1, args.gpus)}",
             "l2": "flushed between timed steps (256 MiB write)"}
 
@@ -213,13 +213,22 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     w = workload_spec(args.workload)
-    n_local = w["n_org"]
-    # every rank draws its own 256 organisms (seed 3 + rank): weak scaling, organism-sharded
-    orgs = build_organisms(args.workload, n_local, 3 + rank)
     pos = synthetic.random_sequences(w["n_pos"], w["seq_len"], 1)
     neg = synthetic.random_sequences(w["n_neg"], w["seq_len"], 2)
     n_seq = len(pos) + len(neg)
-    shards = [np.arange(r * n_local, (r + 1) * n_local) for r in range(world)]
+    if args.scaling == "strong" and world > 1:
+        # the named workload, sharded by organism cost (largest first); every rank builds the same population
+        from flemingo_b200.distributed import organism_costs, shard_by_cost
+        everyone = build_organisms(args.workload, w["n_org"], 3)
+        shards = shard_by_cost(organism_costs(everyone, w["seq_len"]), world)
+        orgs = [everyone[i] for i in shards[rank]]
+        n_total_org = w["n_org"]
+    else:
+        # every rank draws its own population (seed 3 + rank): weak scaling, organism-sharded
+        orgs = build_organisms(args.workload, w["n_org"], 3 + rank)
+        shards = [np.arange(r * w["n_org"], (r + 1) * w["n_org"]) for r in range(world)]
+        n_total_org = w["n_org"] * world
+    n_local = len(orgs)
 
     eng = Engine(local_rank)
     stream = torch.cuda.ExternalStream(eng.stream_handle, device=device)
@@ -287,7 +296,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, place_ms, e2e_s, wall_ms = (float(x) for x in t.cpu())
     if rank == 0:
-        n_org_total = n_local * world
+        n_org_total = n_total_org
         placements = n_org_total * n_seq
         ms_per_step = dev_ms / args.steps
         value = placements / (ms_per_step * 1e-3)
@@ -305,7 +314,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         bytes_alg = k_pairs * ((w["seq_len"] + 3) // 4 + 8)
         hbm_achieved = bytes_alg / (k_ms * 1e-3) / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
+                "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": bench_config(args, w, n_org_total), "clocks": clocks,
                 "e2e": {"value": placements / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s * 1e3},
@@ -342,6 +352,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank owns one full population of the workload (default); strong: the named workload is "
+                         "sharded over the ranks by organism cost (north_star: 2k x 10k in < 100 ms on 8 GPUs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
