@@ -160,7 +160,7 @@ struct Population {
 struct fl_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  DevBuf tables, err_flag, con_begin, org_list, gaps, rsc, csc, fit_out, fit_scratch, fb_count, fb_pairs, fast_scratch, fb_total;
+  DevBuf tables, err_flag, con_begin, org_list, gaps, rsc, csc, fit_out, fit_scratch, fb_count, fb_pairs, fast_scratch, fb_total, work_counters;
   long long fast_pairs = 0, fallback_pairs = 0;  // statistics of the last fl_place_batch
   Population pop, scratch_pop;
   SeqSet sets[FL_MAX_SETS + 1];  // the extra slot serves fl_calculate
@@ -188,6 +188,7 @@ extern "C" int fl_ctx_create(int device, const double *tables, long long n_table
   if (rc == FL_OK) rc = ctx->err_flag.ensure(sizeof(int));
   if (rc == FL_OK) rc = ctx->fb_count.ensure(sizeof(int));
   if (rc == FL_OK) rc = ctx->fb_total.ensure(sizeof(unsigned long long));
+  if (rc == FL_OK) rc = ctx->work_counters.ensure(1024 * sizeof(int));
   if (rc == FL_OK && cudaMemsetAsync(ctx->fb_total.p, 0, sizeof(unsigned long long), ctx->stream) != cudaSuccess) rc = fail(FL_E_CUDA, "memset failed");
   if (rc != FL_OK) {
     delete ctx;
@@ -224,7 +225,7 @@ extern "C" int fl_ctx_destroy(fl_ctx *ctx) {
   }
   release_pop(ctx->pop);
   release_pop(ctx->scratch_pop);
-  DevBuf *bufs[] = {&ctx->tables, &ctx->err_flag, &ctx->con_begin, &ctx->org_list, &ctx->gaps, &ctx->rsc, &ctx->csc, &ctx->fit_out, &ctx->fit_scratch, &ctx->fb_count, &ctx->fb_pairs, &ctx->fast_scratch, &ctx->fb_total};
+  DevBuf *bufs[] = {&ctx->tables, &ctx->err_flag, &ctx->con_begin, &ctx->org_list, &ctx->gaps, &ctx->rsc, &ctx->csc, &ctx->fit_out, &ctx->fit_scratch, &ctx->fb_count, &ctx->fb_pairs, &ctx->fast_scratch, &ctx->fb_total, &ctx->work_counters};
   for (DevBuf *b : bufs) b->release();
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -722,10 +723,14 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
         fp.base.org_list = d_list + fast_begin[j];
         fp.base.seqs_per_cta = spc;
         fp.base.chunks = (cl.count + spc - 1) / spc;
-        const long long grid = (long long)n_b * fp.base.chunks;
-        if (grid > 0x7fffffffLL) return fail(FL_E_UNSUPPORTED, "grid too large");
+        const long long items = (long long)n_b * fp.base.chunks;
+        if (items > 0x7fffffffLL) return fail(FL_E_UNSUPPORTED, "too many work items");
+        const long long grid = std::min<long long>(items, (long long)n_sm * fast_ctas_per_sm[j]);
         if ((rc = ctx->fast_scratch.ensure((size_t)grid * per_round * (size_t)fp.scratch_slot_stride * 4))) return rc;
         fp.scratch = ctx->fast_scratch.as<int>();
+        fp.n_items = (int)items;
+        fp.work_counter = ctx->work_counters.as<int>() + (ctx->launches % 1024);
+        CK(cudaMemsetAsync(fp.work_counter, 0, sizeof(int), ctx->stream));
         kFastConfigs[j].fn<<<(unsigned)grid, nw * 32, fast_smem[j], ctx->stream>>>(fp);
         CK(cudaGetLastError());
         ctx->launches++;

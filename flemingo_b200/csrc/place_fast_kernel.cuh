@@ -41,12 +41,15 @@ struct FastParams {
   int want_trace;
   int *scratch;      // global rows 0..n-3 of every resident pair slot (only the last two rows stay in shared memory)
   long long scratch_slot_stride;  // ints per pair slot in `scratch` (max_rec * rowq_stride)
+  int *work_counter;  // device counter the persistent CTAs claim work items from (zeroed before the launch)
+  int n_items;        // organisms of the bucket x chunks
 };
 
 struct FastPlan {
   double scale;                          // s: quantised = rint(value * s)
   int sent;                              // sentinel ("minus infinity" of the integer pass)
   int ok;                                // 0: this organism cannot use the integer pass
+  int item;                              // work item the CTA is processing (claimed by thread 0)
   int thr_final;                         // slack on the last row
   int thr_pred[FL_MAX_RECOGNIZERS];      // slack on predecessor scans of stage i
   int ngroups[FL_MAX_RECOGNIZERS];       // 4-mer groups of PSSM recognizer i (0 for a shape recognizer)
@@ -562,11 +565,19 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
   constexpr int NT = 32 / TEAM;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const PlaceParams &p = f.base;
-  const int oi = blockIdx.x / p.chunks;
-  const int chunk = blockIdx.x - oi * p.chunks;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int tl = lane % TEAM, team = lane / TEAM;
   const FastSmem sm = carve_fast(f, smem_raw, nwarps, NT);
+  // persistent CTAs: work items (organism x chunk of sequences) are claimed from a device-side counter, so the
+  // global row scratch is sized by the resident CTAs, not by the number of items, and the tail balances itself
+  for (;;) {
+  __syncthreads();
+  if (threadIdx.x == 0) sm.plan->item = atomicAdd(f.work_counter, 1);
+  __syncthreads();
+  const int item = sm.plan->item;
+  if (item >= f.n_items) break;
+  const int oi = item / p.chunks;
+  const int chunk = item - oi * p.chunks;
   const OrgView v = organism_prologue(p, p.org_list[oi], sm.pool, nullptr, sm.rec);
   __syncthreads();
   if (warp == 0) build_fast_plan(f, v, sm, lane);
@@ -637,4 +648,5 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
     }
     __syncwarp();
   }
+  }  // work items
 }
