@@ -275,26 +275,36 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     launches = eng.launch_count - launches0
     clocks = sampler.stop()
 
-    # end to end through the public host API (Python organisms + str sequences in, statistics out)
+    # end to end through the public host API (Python organisms + str sequences in, statistics out).
+    # e2e: EVERYTHING is re-uploaded every step (population and both DNA sets); e2e_resident: the population is
+    # uploaded every step, the DNA sets -- which a GA run never changes between generations -- stay in HBM.
     e2e_steps = max(1, min(args.steps, 5))
-    set_population_fitness(orgs, pos, neg, "Welch", 0.2, engine=eng)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        local = set_population_fitness(orgs, pos, neg, "Welch", 0.2, engine=eng)
-        stats = gather_stats(local, shards, rank, world, device)
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    h2d = int(sum(a.nbytes for a in (packed.rec_begin, packed.rec_type, packed.rec_len, packed.rec_nb, packed.rec_data,
-                                      packed.pool_begin, packed.rec_pool, packed.con_M, packed.con_pool, packed.sum_len))
-              + 2 * ((w["seq_len"] + 15) // 16 * 4 + (w["seq_len"] + 31) // 32 * 4 + 12) * n_seq // 2 + packed.n_org * 8 * 2)
+
+    def e2e_loop(reuse):
+        set_population_fitness(orgs, pos, neg, "Welch", 0.2, engine=eng, reuse_sets=reuse)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            loc = set_population_fitness(orgs, pos, neg, "Welch", 0.2, engine=eng, reuse_sets=reuse)
+            gather_stats(loc, shards, rank, world, device)
+        barrier()
+        return (time.perf_counter() - t0) / e2e_steps
+
+    e2e_s = e2e_loop(False)
+    e2e_res_s = e2e_loop(True)
+    pop_bytes = int(sum(a.nbytes for a in (packed.rec_begin, packed.rec_type, packed.rec_len, packed.rec_nb, packed.rec_data,
+                                           packed.pool_begin, packed.rec_pool, packed.con_M, packed.con_pool, packed.sum_len,
+                                           packed.rec_class, packed.cls_kind, packed.cls_len, packed.cls_nb, packed.cls_edges,
+                                           packed.edges_pool)) + 2 * packed.n_org * 12)
+    seq_bytes = int(n_seq * ((w["seq_len"] + 15) // 16 * 4 + (w["seq_len"] + 31) // 32 * 4 + 17))
+    h2d = pop_bytes + seq_bytes
     d2h = int(packed.n_org * 5 * 8)
 
     # max over ranks
-    t = torch.tensor([dev_ms, place_ms, e2e_s, wall_ms], dtype=torch.float64, device=device)
+    t = torch.tensor([dev_ms, place_ms, e2e_s, wall_ms, e2e_res_s], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, place_ms, e2e_s, wall_ms = (float(x) for x in t.cpu())
+    dev_ms, place_ms, e2e_s, wall_ms, e2e_res_s = (float(x) for x in t.cpu())
     if rank == 0:
         n_org_total = n_total_org
         placements = n_org_total * n_seq
@@ -319,6 +329,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 "data": "synthetic", "config": bench_config(args, w, n_org_total), "clocks": clocks,
                 "e2e": {"value": placements / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s * 1e3},
+                "e2e_resident_sets": {"value": placements / e2e_res_s, "unit": UNIT, "h2d_bytes_per_step": pop_bytes,
+                                      "d2h_bytes_per_step": d2h, "ms_per_step": e2e_res_s * 1e3,
+                                      "note": "population uploaded every step; the two DNA sets stay resident in HBM"},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "alu", "kernel": "place_fast_kernel", "achieved": achieved, "peak": alu_peak,
                              "unit": "TFLOP/s (non-tensor flop-equivalents: 3 per DP cell + 1 per score add)",

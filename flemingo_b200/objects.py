@@ -379,11 +379,11 @@ def place_population(organisms, dna_set, engine=None):
     return out
 
 
-def set_population_fitness(organisms, pos_set, neg_set, method, gamma=0.2, engine=None) -> np.ndarray:
+def set_population_fitness(organisms, pos_set, neg_set, method, gamma=0.2, engine=None, reuse_sets=True) -> np.ndarray:
     """Batched `for org in organisms: org.set_fitness(pos_set, neg_set, method, gamma)`; returns the
     [n_org, 5] statistics (fitness, M_p, SE_p, M_n, SE_n)."""
     eng = engine or get_engine()
-    stats = eng.evaluate(organisms, pos_set, neg_set, method, gamma)
+    stats = eng.evaluate(organisms, pos_set, neg_set, method, gamma, reuse_sets=reuse_sets)
     for org, row in zip(organisms, stats):
         org.fitness = row[0]
     return stats
