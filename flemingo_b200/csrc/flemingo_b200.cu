@@ -21,6 +21,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -80,7 +81,7 @@ struct FastConfig {
 #define FAST_CFG(J, T) {J, T, place_fast_kernel<J, T>}
 static const FastConfig kFastConfigs[] = {
     FAST_CFG(3, 8),  FAST_CFG(5, 8),  FAST_CFG(7, 8),  FAST_CFG(9, 8),  FAST_CFG(11, 8), FAST_CFG(13, 8), FAST_CFG(15, 8),
-    FAST_CFG(17, 8), FAST_CFG(19, 8), FAST_CFG(21, 8), FAST_CFG(13, 16), FAST_CFG(15, 16), FAST_CFG(17, 16), FAST_CFG(19, 16),
+    FAST_CFG(17, 8), FAST_CFG(19, 8), FAST_CFG(21, 8), FAST_CFG(9, 16), FAST_CFG(11, 16), FAST_CFG(13, 16), FAST_CFG(15, 16), FAST_CFG(17, 16), FAST_CFG(19, 16),
     FAST_CFG(21, 16), FAST_CFG(13, 32), FAST_CFG(17, 32), FAST_CFG(21, 32)};
 constexpr int kNumFastConfigs = (int)(sizeof(kFastConfigs) / sizeof(kFastConfigs[0]));
 
@@ -97,6 +98,13 @@ static double fast_cost(int P, int J, int team) {
 static int pick_fast(int P) {
   int best = 0;
   double best_cost = 1e300;
+  // experiments: FLEMINGO_FAST_CFG="J,TEAM" forces one configuration
+  if (const char *force = getenv("FLEMINGO_FAST_CFG")) {
+    int fj = 0, ft = 0;
+    if (sscanf(force, "%d,%d", &fj, &ft) == 2)
+      for (int i = 0; i < kNumFastConfigs; ++i)
+        if (kFastConfigs[i].J == fj && kFastConfigs[i].team == ft) return i;
+  }
   for (int i = 0; i < kNumFastConfigs; ++i) {
     const double c = fast_cost(P, kFastConfigs[i].J, kFastConfigs[i].team);
     if (c < best_cost) {
@@ -653,12 +661,15 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
         const size_t bytes = d * 8 + i * 4 + sizeof(RecDesc) * P.max_rec + sizeof(FastPlan) + 16 + (size_t)nw * nt * fp.k8_stride;
         if (bytes > (size_t)kMaxSmem) continue;
         const int ctas = (int)std::min<size_t>(233472 / (bytes + 1024), 32);
-        const int occ = std::min(ctas * nw, 20);  // ~96 registers per thread cap residency at ~20 warps
+        // ptxas settles at ~100 registers per thread for every tile size (launch bound 512 threads), which caps the
+        // resident warps at 20 per SM
+        const int reg_warps = 20;
+        const int occ = std::min(ctas * nw, reg_warps);
         if (occ > best_occ) {
           best_occ = occ;
           fast_warps[j] = nw;
           fast_smem[j] = bytes;
-          fast_ctas_per_sm[j] = std::max(1, std::min(ctas, 20 / nw));
+          fast_ctas_per_sm[j] = std::max(1, std::min(ctas, reg_warps / nw));
         }
       }
       if (!fast_warps[j]) {
