@@ -144,7 +144,7 @@ struct SeqSet {
   bool valid = false;
   int n_seq = 0;
   std::vector<SeqClass> classes;
-  DevBuf packed, unk, word_off, unk_off, order, has_unk, d_len, bins;
+  DevBuf packed, unk, word_off, unk_off, order, has_unk, d_len, bins, raw, d_offsets;
   int max_len = 0;
   unsigned long long bins_signature = 0;  // shape-class signature the bins were computed for (0 = none)
   long long bins_row_stride = 0;
@@ -229,7 +229,7 @@ extern "C" int fl_ctx_destroy(fl_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (SeqSet &s : ctx->sets) {
-    s.packed.release(); s.unk.release(); s.word_off.release(); s.unk_off.release(); s.order.release(); s.has_unk.release(); s.d_len.release(); s.bins.release(); s.E.release();
+    s.packed.release(); s.unk.release(); s.word_off.release(); s.unk_off.release(); s.order.release(); s.has_unk.release(); s.d_len.release(); s.bins.release(); s.raw.release(); s.d_offsets.release(); s.E.release();
   }
   release_pop(ctx->pop);
   release_pop(ctx->scratch_pop);
@@ -262,21 +262,11 @@ extern "C" int fl_sync(fl_ctx *ctx) {
   return check_device_errors(ctx);
 }
 
-static inline int base_code(char c) {
-  switch (c) {
-    case 'a': case 'A': return 0;
-    case 'g': case 'G': return 1;
-    case 'c': case 'C': return 2;
-    case 't': case 'T': return 3;
-    default: return -1;
-  }
-}
-
 static int upload_sequences(fl_ctx *ctx, SeqSet &set, const char *bytes, const long long *offsets, int n_seq) {
   if (n_seq < 0 || (n_seq > 0 && (!bytes || !offsets))) return fail(FL_E_ARG, "fl_upload_sequences: bad arguments");
   std::vector<int> len(n_seq), word_off(n_seq), unk_off(n_seq), order(n_seq);
-  std::vector<unsigned char> has_unk((size_t)n_seq + 1, 0);
   long long words = 0, uwords = 0;
+  bool one_length = true;
   for (int s = 0; s < n_seq; ++s) {
     const long long l = offsets[s + 1] - offsets[s];
     if (l < 0 || l > 100000000) return fail(FL_E_ARG, "fl_upload_sequences: sequence %d has length %lld", s, l);
@@ -287,22 +277,9 @@ static int upload_sequences(fl_ctx *ctx, SeqSet &set, const char *bytes, const l
     uwords += (l + 31) / 32;
     if (words > 0x7fffffffLL) return fail(FL_E_ARG, "fl_upload_sequences: set too large");
     order[s] = s;
+    one_length = one_length && (len[s] == len[0]);
   }
-  std::vector<unsigned> packed((size_t)words + 1, 0u), unk((size_t)uwords + 1, 0u);
-  for (int s = 0; s < n_seq; ++s) {
-    const char *b = bytes + offsets[s];
-    unsigned *pw = packed.data() + word_off[s];
-    unsigned *uw = unk.data() + unk_off[s];
-    for (int i = 0; i < len[s]; ++i) {
-      const int c = base_code(b[i]);
-      if (c < 0) {
-        uw[i >> 5] |= 1u << (i & 31);
-        has_unk[s] = 1;
-      }
-      else pw[i >> 4] |= (unsigned)c << (2 * (i & 15));
-    }
-  }
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return len[a] < len[b]; });
+  if (!one_length) std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return len[a] < len[b]; });
   set.classes.clear();
   for (int i = 0; i < n_seq; ++i) {
     const int l = len[order[i]];
@@ -310,22 +287,32 @@ static int upload_sequences(fl_ctx *ctx, SeqSet &set, const char *bytes, const l
     set.classes.back().count++;
   }
   set.n_seq = n_seq;
+  const size_t raw_bytes = n_seq ? (size_t)(offsets[n_seq] - offsets[0]) : 0;
   int rc;
-  if ((rc = set.packed.ensure(packed.size() * 4)) || (rc = set.unk.ensure(unk.size() * 4)) ||
+  if ((rc = set.packed.ensure(((size_t)words + 2) * 4)) || (rc = set.unk.ensure(((size_t)uwords + 2) * 4)) ||
       (rc = set.word_off.ensure((size_t)n_seq * 4 + 4)) || (rc = set.unk_off.ensure((size_t)n_seq * 4 + 4)) ||
       (rc = set.order.ensure((size_t)n_seq * 4 + 4)) || (rc = set.has_unk.ensure((size_t)n_seq + 4)) ||
-      (rc = set.d_len.ensure((size_t)n_seq * 4 + 4)))
+      (rc = set.d_len.ensure((size_t)n_seq * 4 + 4)) || (rc = set.raw.ensure(raw_bytes + 16)) ||
+      (rc = set.d_offsets.ensure(((size_t)n_seq + 1) * 8)))
     return rc;
-  CK(cudaMemcpyAsync(set.packed.p, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(set.unk.p, unk.data(), unk.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
   if (n_seq) {
+    // raw bytes go up as they are; the 2-bit packing runs on the device (pack_sequences_kernel)
+    std::vector<long long> rel((size_t)n_seq + 1);
+    for (int s = 0; s <= n_seq; ++s) rel[s] = offsets[s] - offsets[0];
+    CK(cudaMemcpyAsync(set.raw.p, bytes + offsets[0], raw_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(set.d_offsets.p, rel.data(), ((size_t)n_seq + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(set.word_off.p, word_off.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(set.unk_off.p, unk_off.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(set.order.p, order.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(set.has_unk.p, has_unk.data(), (size_t)n_seq, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(set.d_len.p, len.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, ctx->stream));
+    pack_sequences_kernel<<<(unsigned)n_seq, 64, 0, ctx->stream>>>(set.raw.as<unsigned char>(), set.d_offsets.as<long long>(),
+                                                                    set.word_off.as<int>(), set.unk_off.as<int>(),
+                                                                    set.packed.as<unsigned>(), set.unk.as<unsigned>(),
+                                                                    set.has_unk.as<unsigned char>());
+    CK(cudaGetLastError());
+    ctx->launches++;
+    CK(cudaStreamSynchronize(ctx->stream));  // the staging vectors die at return
   }
-  CK(cudaStreamSynchronize(ctx->stream));  // the staging vectors die at return
   set.max_len = 0;
   for (int s2 = 0; s2 < n_seq; ++s2) set.max_len = std::max(set.max_len, len[s2]);
   set.bins_signature = 0;

@@ -81,3 +81,48 @@ __global__ void __launch_bounds__(128) shape_bins_kernel(const ShapeBinParams q)
     out[p] = (unsigned char)(b - 1);
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// 2-bit packing of a DNA set on the device: the host uploads the raw ASCII bytes once, one CTA per sequence packs
+// 16 bases per 32-bit word (A=0, G=1, C=2, T=3, case-insensitive, recognizer.c:143-163) plus a 1-bit "unknown byte"
+// mask, and flags sequences that contain a non-ACGT byte.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned base_code_dev(unsigned char c) {
+  switch (c | 0x20) {   // lower case
+    case 'a': return 0u;
+    case 'g': return 1u;
+    case 'c': return 2u;
+    case 't': return 3u;
+    default: return 4u;
+  }
+}
+
+__global__ void __launch_bounds__(64) pack_sequences_kernel(const unsigned char *__restrict__ raw, const long long *__restrict__ offsets,
+                                                            const int *__restrict__ word_off, const int *__restrict__ unk_off,
+                                                            unsigned *__restrict__ packed, unsigned *__restrict__ unk,
+                                                            unsigned char *__restrict__ has_unk) {
+  const int seq = blockIdx.x;
+  const unsigned char *b = raw + offsets[seq];
+  const int len = (int)(offsets[seq + 1] - offsets[seq]);
+  unsigned *pw = packed + word_off[seq];
+  unsigned *uw = unk + unk_off[seq];
+  int any = 0;
+  // one thread per unknown-mask word = 32 bases = two packed words
+  for (int u = threadIdx.x; u * 32 < len; u += blockDim.x) {
+    unsigned lo = 0u, hi = 0u, mask = 0u;
+    const int base = u * 32;
+    const int cnt = min(32, len - base);
+    for (int i = 0; i < cnt; ++i) {
+      const unsigned c = base_code_dev(b[base + i]);
+      if (c > 3u) mask |= 1u << i;
+      else if (i < 16) lo |= c << (2 * i);
+      else hi |= c << (2 * (i - 16));
+    }
+    uw[u] = mask;
+    pw[2 * u] = lo;
+    if (base + 16 < len) pw[2 * u + 1] = hi;
+    any |= (mask != 0u);
+  }
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) has_unk[seq] = any ? 1 : 0;
+}

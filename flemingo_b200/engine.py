@@ -31,9 +31,6 @@ class SequenceSet:
     class_len: list          # distinct lengths, ascending (the library's class order)
     sequences: list          # the caller's strings (kept for PlacementObject construction)
     blob: bytes = b""        # the uploaded bytes (to recognise an unchanged dataset)
-    sequences_ref: object = None
-    first: object = None
-    last: object = None
 
 
 @dataclass
@@ -95,27 +92,26 @@ class Engine:
     def upload_sequences(self, sequences, set_id: int = 0, reuse: bool = False) -> SequenceSet:
         """Uploads a DNA set (list of str/bytes); bases are 2-bit packed on the way (fl_upload_sequences).
 
-        reuse=True skips the upload when the set resident under set_id holds the same sequences (same list object
-        with the same first/last elements, or equal bytes): the GA evaluates thousands of generations on one
-        dataset, so the packed copy stays in HBM across calls.
+        reuse=True skips the upload when the set resident under set_id holds byte-for-byte the same sequences: the
+        GA evaluates thousands of generations on one dataset, so the packed copy stays in HBM across calls.
         """
         old = self._sets.get(set_id)
-        if reuse and old is not None and old.sequences_ref is sequences and len(sequences) == old.n_seq and \
-                (old.n_seq == 0 or (sequences[0] is old.first and sequences[-1] is old.last)):
-            return old
-        seqs = [s if isinstance(s, (bytes, bytearray)) else bytes(s, "ASCII") for s in sequences]
-        lengths = np.fromiter((len(s) for s in seqs), dtype=np.int64, count=len(seqs))
+        seqs = sequences
+        lengths = np.fromiter(map(len, seqs), dtype=np.int64, count=len(seqs))
+        try:
+            joined = "".join(seqs).encode("ascii")          # the common case: a list of str
+        except TypeError:
+            joined = b"".join(s if isinstance(s, (bytes, bytearray)) else bytes(s, "ASCII") for s in seqs)
         offsets = np.zeros(len(seqs) + 1, dtype=np.int64)
         np.cumsum(lengths, out=offsets[1:])
-        joined = b"".join(seqs)
+        if offsets[-1] != len(joined):
+            raise ValueError("sequences must be ASCII")
         if reuse and old is not None and old.n_seq == len(seqs) and old.blob == joined and np.array_equal(old.lengths, lengths):
-            old.sequences_ref, old.first, old.last = sequences, (sequences[0] if seqs else None), (sequences[-1] if seqs else None)
             return old
         blob = np.frombuffer(joined + b"\0", dtype=np.uint8)
         _cabi.check(self._lib.fl_upload_sequences(self._ctx, set_id, _ptr(blob), _ptr(offsets), len(seqs)))
         sset = SequenceSet(set_id=set_id, n_seq=len(seqs), lengths=lengths,
-                           class_len=sorted(set(int(x) for x in lengths)), sequences=list(sequences), blob=joined,
-                           sequences_ref=sequences, first=(sequences[0] if seqs else None), last=(sequences[-1] if seqs else None))
+                           class_len=sorted(set(int(x) for x in lengths)), sequences=list(sequences), blob=joined)
         self._sets[set_id] = sset
         return sset
 
