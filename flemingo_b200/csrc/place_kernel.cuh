@@ -136,7 +136,7 @@ __device__ __forceinline__ double gap_energy(const double *__restrict__ pdf, dou
 // (R_i[j] is added afterwards by the caller; fl(max + r) == max fl(. + r) because x -> fl(x+r) is monotone.)
 // Op selects the arithmetic: exact double (DADD + compare/select) or int32 fixed point (one DPX VIADDMNMX).
 // G points at gap 0 and is readable on [-kGPad, P-1+kGPad] with `lowest` outside [0, P).
-// prev must be readable up to ceil(P/J)*J - 1; for doubles the values beyond P-1 are never selected because
+// prev must be readable and cur writable up to ceil(P/J)*J - 1; for doubles the values beyond P-1 are never selected because
 // their G is -inf, for ints the caller keeps them at 0 so that 0 + lowest cannot wrap.
 // ------------------------------------------------------------------------------------------------
 struct OpF64 {
@@ -167,10 +167,10 @@ __device__ __forceinline__ void tile_step(typename Op::T (&A)[J], typename Op::T
   typedef typename Op::T T;
   if (st.kb == st.kend) {
     // job finished: flush its rows, then start the folded partner block (or idle)
-    const int r0 = st.b * J;
+    // rows beyond P-1 of the last block land in the row's padding (the caller owns >= ceil(P/J)*J entries)
+    typename Op::T *dst = cur + st.b * J;
 #pragma unroll
-    for (int t = 0; t < J; ++t)
-      if (r0 + t < P) cur[r0 + t] = acc[t];
+    for (int t = 0; t < J; ++t) dst[t] = acc[t];
     if (st.next_b >= 0) {
       st.b = st.next_b;
       st.next_b = -1;
@@ -247,10 +247,9 @@ __device__ __forceinline__ void dp_stage(const typename Op::T *__restrict__ prev
       tile_step<J, Op>(B, A, acc, st, prev, cur, G, P, lowest);
     }
     if (st.kstep) {  // the last job of this lane has not been flushed by a later step
-      const int rr = st.b * J;
+      T *dst = cur + st.b * J;
 #pragma unroll
-      for (int t = 0; t < J; ++t)
-        if (rr + t < P) cur[rr + t] = acc[t];
+      for (int t = 0; t < J; ++t) dst[t] = acc[t];
     }
   }
 }
