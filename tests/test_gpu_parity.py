@@ -289,3 +289,25 @@ def test_full_size_config3_sample_vs_oracle(engine):
     orgs = synthetic.mixed_organisms(120, 300, 3)
     seqs = synthetic.random_sequences(40, 300, 1)
     _assert_equals_oracle(engine, orgs, seqs)
+
+
+def test_adversarial_population_fast_path_equals_exact_path_and_oracle(engine):
+    """Adversarial organisms x low-complexity sequences (tests/helpers.adversarial_workload): the two GPU paths agree on
+    every pair and a sample equals the CPU oracle."""
+    from tests.helpers import adversarial_workload
+    orgs, seqs = adversarial_workload(11, 150, n_seq=60)
+    engine.upload_population(orgs)
+    sset = engine.upload_sequences(seqs, 0)
+    mine = engine.place(sset, trace=True)
+    was = engine.exact_only
+    engine.exact_only = not was
+    other = engine.place(sset, trace=True)
+    engine.exact_only = was
+    for k in ("energies", "gaps", "rec_scores", "con_scores"):
+        assert np.array_equal(getattr(mine, k), getattr(other, k)), k
+    rng = np.random.default_rng(3)
+    for o, s in zip(rng.integers(0, len(orgs), 150), rng.integers(0, len(seqs), 150)):
+        e, rs, cs, gaps, _ = oracle.place(orgs[o], seqs[s])
+        n = len(orgs[o].recognizer_types)
+        assert mine.energies[o, s] == e and np.array_equal(mine.gaps[o, s, :n], gaps)
+        assert np.array_equal(mine.rec_scores[o, s, :n], rs) and np.array_equal(mine.con_scores[o, s, :n - 1], cs)
