@@ -58,7 +58,7 @@ struct FastPlan {
 };
 
 struct FastSmem {
-  double *pool, *cv, *cr;
+  double *pool, *G, *cv, *cr;
   int *Gq, *kmer, *rowsq, *cj, *ca, *cn;
   unsigned *seqw, *bitmap;
   unsigned char *k8;
@@ -70,7 +70,8 @@ __device__ __forceinline__ FastSmem carve_fast(const FastParams &f, unsigned cha
   const PlaceParams &p = f.base;
   FastSmem s;
   s.pool = reinterpret_cast<double *>(raw);
-  s.cv = s.pool + p.pool_stride;
+  s.G = s.pool + p.pool_stride;                       // exact gap energies [max_rec-1][g_stride], -inf outside [0, P)
+  s.cv = s.G + (size_t)(p.max_rec - 1) * p.g_stride;
   s.cr = s.cv + (size_t)nwarps * p.max_rec * kCandCap;
   s.plan = reinterpret_cast<FastPlan *>(s.cr + (size_t)nwarps * p.max_rec * kCandCap);
   s.rec = reinterpret_cast<RecDesc *>(s.plan + 1);
@@ -199,10 +200,10 @@ __device__ void build_fast_plan(const FastParams &f, const OrgView &v, const Fas
     range += hi - lo;
   }
   for (int c = 0; c < n - 1; ++c) {
-    const ConView cvw = connector_view(p, v, c);
+    const double *Gc = sm.G + (size_t)c * p.g_stride + kGPad;
     double lo = inf, hi = -inf;
     for (int g = lane; g <= P - 2; g += 32) {  // legit gaps; g = P-1 is the reference's -1e10 sentinel
-      const double x = exact_gap(p, v, cvw, g);
+      const double x = Gc[g];
       lo = fmin(lo, x);
       hi = fmax(hi, x);
       bad |= (x != x);
@@ -287,11 +288,11 @@ __device__ void build_fast_plan(const FastParams &f, const OrgView &v, const Fas
     }
     lo_q_rec = lo_q;
     for (int c = 0; c < n - 1; ++c) {
-      const ConView cvw = connector_view(p, v, c);
+      const double *Gc = sm.G + (size_t)c * p.g_stride + kGPad;
       int *Gq = sm.Gq + (size_t)c * f.gq_stride + kGPad;
       int lo = 0x7fffffff, hi = -0x7fffffff;
       for (int g = lane; g <= P - 2; g += 32) {
-        const int q = __double2int_rn(exact_gap(p, v, cvw, g) * s);
+        const int q = __double2int_rn(Gc[g] * s);
         Gq[g] = q;
         lo = min(lo, q);
         hi = max(hi, q);
@@ -359,19 +360,29 @@ __device__ bool refine_pair(const FastParams &f, const OrgView &v, const FastSme
   {
     const int *row = row_q(f, n, n - 1, rowsq, rowsg);
     int mx = -0x7fffffff;
+#pragma unroll 4
     for (int j = lane; j < P; j += 32) mx = max(mx, row[j]);
     mx = warp_max_i(mx);
     const int thr = mx - plan.thr_final;
     int count = 0;
-    for (int base = 0; base < P; base += 32) {
-      const int j = base + lane;
-      const bool pred = (j < P) && (row[j] >= thr);
-      const unsigned bal = __ballot_sync(0xffffffffu, pred);
-      if (pred) {
-        const int idx = count + __popc(bal & lt_mask);
-        if (idx < kCandCap) cj[(n - 1) * kCandCap + idx] = j;
+    // four 32-wide groups per trip: the loads are issued together, then the ballots
+    for (int base = 0; base < P; base += 128) {
+      int x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = base + 32 * u + lane;
+        x[u] = (j < P) ? row[j] : -0x7fffffff - 1;
       }
-      count += __popc(bal);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool pred = x[u] >= thr;
+        const unsigned bal = __ballot_sync(0xffffffffu, pred);
+        if (pred) {
+          const int idx = count + __popc(bal & lt_mask);
+          if (idx < kCandCap) cj[(n - 1) * kCandCap + idx] = base + 32 * u + lane;
+        }
+        count += __popc(bal);
+      }
     }
     if (count > kCandCap) return false;
     if (lane == 0) cn[n - 1] = count;
@@ -390,15 +401,23 @@ __device__ bool refine_pair(const FastParams &f, const OrgView &v, const FastSme
       // the usual case: one candidate, its predecessors are compacted straight from the scan
       const int j = cj[i * kCandCap];
       const int thr = (cur[j] - score_q_any(plan, i, rdi, sm.kmer, k8, bins_seq, cls_stride, j)) - plan.thr_pred[i];
-      for (int base = 0; base <= j; base += 32) {
-        const int k = base + lane;
-        const bool pred = (k <= j) && (prev[k] + Gq[j - k] >= thr);
-        const unsigned bal = __ballot_sync(0xffffffffu, pred);
-        if (pred) {
-          const int idx = count + __popc(bal & lt_mask);
-          if (idx < kCandCap) cj[(i - 1) * kCandCap + idx] = k;
+      for (int base = 0; base <= j; base += 128) {
+        int x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = base + 32 * u + lane;
+          x[u] = (k <= j) ? prev[k] + Gq[j - k] : -0x7fffffff - 1;
         }
-        count += __popc(bal);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool pred = x[u] >= thr;
+          const unsigned bal = __ballot_sync(0xffffffffu, pred);
+          if (pred) {
+            const int idx = count + __popc(bal & lt_mask);
+            if (idx < kCandCap) cj[(i - 1) * kCandCap + idx] = base + 32 * u + lane;
+          }
+          count += __popc(bal);
+        }
       }
     } else {
       // several candidates: union of their predecessor sets through a bitmap (sorted and duplicate free)
@@ -456,14 +475,14 @@ __device__ bool refine_pair(const FastParams &f, const OrgView &v, const FastSme
     if (lane < cn[i]) {
       const int j = cj[i * kCandCap + lane];
       const double rj = cr[i * kCandCap + lane];
-      const ConView cvw = connector_view(p, v, i - 1);
+      const double *G = sm.G + (size_t)(i - 1) * p.g_stride + kGPad;
       double best = neg_inf();
       int arg = -1;
       const int np = cn[i - 1];
       for (int d = 0; d < np; ++d) {  // ascending k: the first k that attains the maximum wins (organism.c:365)
         const int k = cj[(i - 1) * kCandCap + d];
         if (k <= j) {
-          const double cand = (cv[(i - 1) * kCandCap + d] + exact_gap(p, v, cvw, j - k)) + rj;
+          const double cand = (cv[(i - 1) * kCandCap + d] + G[j - k]) + rj;
           if (best < cand) {
             best = cand;
             arg = d;
@@ -490,7 +509,7 @@ __device__ bool refine_pair(const FastParams &f, const OrgView &v, const FastSme
         const int k = cj[(i - 1) * kCandCap + (d < 0 ? 0 : d)];
         const int gap = d < 0 ? 0 : j - k;
         p.rsc[pair * p.max_rec + i] = cr[i * kCandCap + c];
-        p.csc[pair * p.max_rec + i - 1] = d < 0 ? 0.0 : exact_gap(p, v, connector_view(p, v, i - 1), gap);
+        p.csc[pair * p.max_rec + i - 1] = d < 0 ? 0.0 : sm.G[(size_t)(i - 1) * p.g_stride + kGPad + gap];
         p.gaps[pair * p.max_rec + i] = gap;
         c = d < 0 ? 0 : d;
       }
@@ -578,7 +597,7 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
   if (item >= f.n_items) break;
   const int oi = item / p.chunks;
   const int chunk = item - oi * p.chunks;
-  const OrgView v = organism_prologue(p, p.org_list[oi], sm.pool, nullptr, sm.rec);
+  const OrgView v = organism_prologue(p, p.org_list[oi], sm.pool, sm.G, sm.rec);
   __syncthreads();
   if (warp == 0) build_fast_plan(f, v, sm, lane);
   __syncthreads();
