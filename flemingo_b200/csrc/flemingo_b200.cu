@@ -702,7 +702,8 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
       if ((rc = ctx->fb_pairs.ensure((size_t)cap * sizeof(int2)))) return rc;
       fp.fb_count = ctx->fb_count.as<int>();
       fp.fb_pairs = ctx->fb_pairs.as<int2>();
-      fp.fb_cap = (int)std::min<long long>(cap, 0x7fffffffLL);
+      if (cap > 0x7fffffffLL) return fail(FL_E_UNSUPPORTED, "%lld pairs in one length class exceed the hand-back list (2^31-1); split the population or the set", cap);
+      fp.fb_cap = (int)cap;
       CK(cudaMemsetAsync(ctx->fb_count.p, 0, sizeof(int), ctx->stream));
       for (int j = 0; j < kNumFastConfigs; ++j) {
         const int n_b = (int)fast_bucket[j].size();
