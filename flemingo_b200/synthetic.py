@@ -111,6 +111,9 @@ WORKLOADS = {
     "c2": dict(kind="pssm", n_org=256, n_pos=1000, n_neg=1000, seq_len=300),
     "c3": dict(kind="mixed", n_org=2000, n_pos=5000, n_neg=5000, seq_len=300),
     "c4": dict(kind="pssm", n_org=512, n_pos=2500, n_neg=2500, seq_len=2000, mu_range=(0, 1500)),
+    # config 5: one generation of the 4k-population GA run (every step re-uploads the population, as a generation
+    # of new children would); the mutation / crowding operators themselves are host logic outside the hot path
+    "c5": dict(kind="mixed", n_org=4096, n_pos=20000, n_neg=20000, seq_len=300),
 }
 
 
