@@ -644,7 +644,7 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
       for (int nw : kWarpChoices) {
         const size_t d = (size_t)pp.pool_stride + (size_t)(P.max_rec - 1) * pp.g_stride + 2ull * nw * P.max_rec * kCandCap;
         const size_t i = (size_t)(P.max_rec - 1) * fp.gq_stride + fp.kmer_cap + (size_t)nw * nt * fast_slot[j] + (size_t)nw * nt * fp.seqw_stride +
-                         2ull * nw * P.max_rec * kCandCap + (size_t)nw * P.max_rec + (size_t)nw * fp.bitmap_words;
+                         2ull * nw * P.max_rec * kCandCap + (size_t)nw * nt * P.max_rec + (size_t)nw * fp.bitmap_words;
         const size_t bytes = d * 8 + i * 4 + sizeof(RecDesc) * P.max_rec + sizeof(FastPlan) + 16 + (size_t)nw * nt * fp.k8_stride;
         if (bytes > (size_t)kMaxSmem) continue;
         const int ctas = (int)std::min<size_t>(233472 / (bytes + 1024), 32);

@@ -21,7 +21,7 @@
 // which makes this legal here and illegal in the exact pass.
 #pragma once
 
-constexpr int kCandCap = 16;   // candidates kept per stage before a pair is handed to the exact kernel
+constexpr int kCandCap = 16;   // candidate cells per stage shared by the pairs of a warp (16 / pairs-per-warp each)
 constexpr int kNanBinMarker = (int)0x80000000;  // quantised score of a bin whose null frequency is NaN
 constexpr int kSlackUnits = 2; // covers fp64-vs-real rounding of the reference sums (<< 1 unit) with margin
 
@@ -82,7 +82,7 @@ __device__ __forceinline__ FastSmem carve_fast(const FastParams &f, unsigned cha
   s.cj = reinterpret_cast<int *>(s.seqw + (size_t)nwarps * nt * f.seqw_stride);
   s.ca = s.cj + (size_t)nwarps * p.max_rec * kCandCap;
   s.cn = s.ca + (size_t)nwarps * p.max_rec * kCandCap;
-  s.bitmap = reinterpret_cast<unsigned *>(s.cn + (size_t)nwarps * p.max_rec);
+  s.bitmap = reinterpret_cast<unsigned *>(s.cn + (size_t)nwarps * nt * p.max_rec);
   s.k8 = reinterpret_cast<unsigned char *>(s.bitmap + (size_t)nwarps * f.bitmap_words);
   return s;
 }
@@ -333,192 +333,286 @@ __device__ void build_fast_plan(const FastParams &f, const OrgView &v, const Fas
   }
 }
 
-// ---- exact refinement of one pair on its candidate sets (whole warp) -----------------------------------
-// rowsq: the pair's quantised rows [n][rowq_stride]; w: its packed sequence.  Returns false if a candidate set
-// overflowed (pair goes to the exact kernel).
+// ---- exact refinement of the warp's NT pairs on their candidate sets ---------------------------------------------
+// The NT pairs a warp has just pushed through the integer pass are refined TOGETHER: every step is written over the
+// pair index t so that the NT dependency chains (row maxima, warp votes, score chains) interleave, and the per-pair
+// scalar work (exact recurrence, outputs) runs on NT lanes at once instead of NT times on one lane.
+// Candidate lists hold kCandCap / NT cells per stage and pair; a pair that needs more is handed to the exact kernel.
 // Quantised row i of a pair: the last two stages are still in the shared ping-pong buffers, older ones in global scratch.
 __device__ __forceinline__ const int *row_q(const FastParams &f, int n, int i, const int *rows_smem, const int *rows_glob) {
   return (i >= n - 2) ? rows_smem + (size_t)(i & 1) * f.rowq_stride : rows_glob + (size_t)i * f.rowq_stride;
 }
 
-__device__ bool refine_pair(const FastParams &f, const OrgView &v, const FastSmem &sm, const int *rowsq, const int *rowsg,
-                            const unsigned *w, const unsigned char *k8, int seq, int warp, int lane) {
+template <int NT>
+__device__ __forceinline__ void refine_round(const FastParams &f, const OrgView &v, const FastSmem &sm, int warp, int lane,
+                                             int nwarps, const int (&seq)[NT], const bool (&active)[NT], bool (&failed)[NT]) {
+  constexpr int CAP = kCandCap / NT;
+  constexpr int kLowest = -0x7fffffff - 1;
   const PlaceParams &p = f.base;
   const FastPlan &plan = *sm.plan;
   const int n = v.n, P = v.P;
+  // per-warp candidate storage, indexed [t][stage][c]
   int *cj = sm.cj + (size_t)warp * p.max_rec * kCandCap;
   int *ca = sm.ca + (size_t)warp * p.max_rec * kCandCap;
-  int *cn = sm.cn + (size_t)warp * p.max_rec;
+  int *cn = sm.cn + (size_t)warp * NT * p.max_rec;
   double *cv = sm.cv + (size_t)warp * p.max_rec * kCandCap;
   double *cr = sm.cr + (size_t)warp * p.max_rec * kCandCap;
   unsigned *bitmap = sm.bitmap + (size_t)warp * f.bitmap_words;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const unsigned char *bins_seq = p.bins + (size_t)seq * p.bins_row_stride;
   const size_t cls_stride = (size_t)p.n_seq_total * p.bins_row_stride;
-
-  // (1) candidates on the last row
-  {
-    const int *row = row_q(f, n, n - 1, rowsq, rowsg);
-    int mx = -0x7fffffff;
-#pragma unroll 4
-    for (int j = lane; j < P; j += 32) mx = max(mx, row[j]);
-    mx = warp_max_i(mx);
-    const int thr = mx - plan.thr_final;
-    int count = 0;
-    // four 32-wide groups per trip: the loads are issued together, then the ballots
-    for (int base = 0; base < P; base += 128) {
-      int x[4];
+  auto at = [&](int t, int i, int c) { return (t * p.max_rec + i) * CAP + c; };
+  // value of a small per-pair register array at a lane-dependent pair index (select chain, no local memory)
+  auto pick = [&](const int (&a)[NT], int t) {
+    int r = a[0];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int j = base + 32 * u + lane;
-        x[u] = (j < P) ? row[j] : -0x7fffffff - 1;
+    for (int tt = 1; tt < NT; ++tt) r = (t == tt) ? a[tt] : r;
+    return r;
+  };
+
+  const int *rows[NT];
+  const int *rowg[NT];
+  const unsigned *w[NT];
+  const unsigned char *k8[NT];
+  const unsigned char *bins[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const int slot = warp * NT + t;
+    rows[t] = sm.rowsq + (size_t)slot * f.slotq_stride;
+    rowg[t] = f.scratch + ((size_t)blockIdx.x * nwarps * NT + slot) * f.scratch_slot_stride;
+    w[t] = sm.seqw + (size_t)slot * f.seqw_stride;
+    k8[t] = sm.k8 + (size_t)slot * f.k8_stride;
+    bins[t] = p.bins + (size_t)seq[t] * p.bins_row_stride;
+    failed[t] = false;
+  }
+
+  // (1) candidates on the last row: maxima of the NT rows in one sweep, then one compaction sweep
+  {
+    const int *row[NT];
+    int mx[NT], thr[NT], count[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      row[t] = row_q(f, n, n - 1, rows[t], rowg[t]);
+      mx[t] = kLowest;
+      count[t] = 0;
+    }
+#pragma unroll 2
+    for (int j = lane; j < P; j += 32) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) mx[t] = max(mx[t], row[t][j]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) mx[t] = max(mx[t], __shfl_xor_sync(0xffffffffu, mx[t], o));
+    }
+#pragma unroll
+    for (int t = 0; t < NT; ++t) thr[t] = mx[t] - plan.thr_final;
+    for (int base = 0; base < P; base += 64) {
+      int x[NT][2];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int j = base + 32 * u + lane;
+          x[t][u] = (j < P) ? row[t][j] : kLowest;
+        }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const bool pred = x[u] >= thr;
-        const unsigned bal = __ballot_sync(0xffffffffu, pred);
-        if (pred) {
-          const int idx = count + __popc(bal & lt_mask);
-          if (idx < kCandCap) cj[(n - 1) * kCandCap + idx] = base + 32 * u + lane;
+      for (int t = 0; t < NT; ++t) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const bool pred = x[t][u] >= thr[t];
+          const unsigned bal = __ballot_sync(0xffffffffu, pred);
+          if (pred) {
+            const int idx = count[t] + __popc(bal & lt_mask);
+            if (idx < CAP) cj[at(t, n - 1, idx)] = base + 32 * u + lane;
+          }
+          count[t] += __popc(bal);
         }
-        count += __popc(bal);
       }
     }
-    if (count > kCandCap) return false;
-    if (lane == 0) cn[n - 1] = count;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      if (count[t] > CAP) failed[t] = true;
+      if (lane == 0) cn[t * p.max_rec + n - 1] = min(count[t], CAP);
+    }
   }
   __syncwarp();
+
   // (2) candidate sets of the earlier stages, top down
   const int words = (P + 31) >> 5;
   for (int i = n - 1; i >= 1; --i) {
-    const int *prev = row_q(f, n, i - 1, rowsq, rowsg);
-    const int *cur = row_q(f, n, i, rowsq, rowsg);
     const int *Gq = sm.Gq + (size_t)(i - 1) * f.gq_stride + kGPad;
     const RecDesc rdi = sm.rec[i];
-    const int cnt = cn[i];
-    int count = 0;
-    if (cnt == 1) {
-      // the usual case: one candidate, its predecessors are compacted straight from the scan
-      const int j = cj[i * kCandCap];
-      const int thr = (cur[j] - score_q_any(plan, i, rdi, sm.kmer, k8, bins_seq, cls_stride, j)) - plan.thr_pred[i];
-      for (int base = 0; base <= j; base += 128) {
-        int x[4];
+    const int *prev[NT];
+    int cnt[NT], count[NT];
+    bool all_single = true;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int k = base + 32 * u + lane;
-          x[u] = (k <= j) ? prev[k] + Gq[j - k] : -0x7fffffff - 1;
+    for (int t = 0; t < NT; ++t) {
+      prev[t] = row_q(f, n, i - 1, rows[t], rowg[t]);
+      cnt[t] = (active[t] && !failed[t]) ? cn[t * p.max_rec + i] : 0;
+      count[t] = 0;
+      all_single = all_single && (cnt[t] <= 1);
+    }
+    if (all_single) {
+      // the usual case: at most one candidate per pair; the NT predecessor scans run side by side
+      int j[NT], thr[NT], jmax = -1;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        j[t] = cnt[t] ? cj[at(t, i, 0)] : -1;
+        const int *cur = row_q(f, n, i, rows[t], rowg[t]);
+        thr[t] = cnt[t] ? (cur[j[t]] - score_q_any(plan, i, rdi, sm.kmer, k8[t], bins[t], cls_stride, j[t])) - plan.thr_pred[i] : 0;
+        jmax = max(jmax, j[t]);
+      }
+      for (int base = 0; base <= jmax; base += 64) {
+        int x[NT][2];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int k = base + 32 * u + lane;
+            x[t][u] = (k <= j[t]) ? prev[t][k] + Gq[j[t] - k] : kLowest;
+          }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const bool pred = x[u] >= thr;
-          const unsigned bal = __ballot_sync(0xffffffffu, pred);
-          if (pred) {
-            const int idx = count + __popc(bal & lt_mask);
-            if (idx < kCandCap) cj[(i - 1) * kCandCap + idx] = base + 32 * u + lane;
+        for (int t = 0; t < NT; ++t) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const bool pred = (x[t][u] >= thr[t]) && (base + 32 * u + lane <= j[t]);
+            const unsigned bal = __ballot_sync(0xffffffffu, pred);
+            if (pred) {
+              const int idx = count[t] + __popc(bal & lt_mask);
+              if (idx < CAP) cj[at(t, i - 1, idx)] = base + 32 * u + lane;
+            }
+            count[t] += __popc(bal);
           }
-          count += __popc(bal);
         }
       }
     } else {
-      // several candidates: union of their predecessor sets through a bitmap (sorted and duplicate free)
-      for (int t = lane; t < words; t += 32) bitmap[t] = 0u;
-      __syncwarp();
-      for (int c = 0; c < cnt; ++c) {
-        const int j = cj[i * kCandCap + c];
-        const int thr = (cur[j] - score_q_any(plan, i, rdi, sm.kmer, k8, bins_seq, cls_stride, j)) - plan.thr_pred[i];
-        for (int base = 0; base <= j; base += 32) {
-          const int k = base + lane;
-          const bool pred = (k <= j) && (prev[k] + Gq[j - k] >= thr);
-          const unsigned bal = __ballot_sync(0xffffffffu, pred);
-          if (lane == 0 && bal) bitmap[base >> 5] |= bal;
+      // several candidates somewhere: pair by pair, union of the predecessor sets through a bitmap (sorted, no duplicates)
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        if (cnt[t] == 0) continue;
+        const int *cur = row_q(f, n, i, rows[t], rowg[t]);
+        for (int q = lane; q < words; q += 32) bitmap[q] = 0u;
+        __syncwarp();
+        for (int c = 0; c < cnt[t]; ++c) {
+          const int jj = cj[at(t, i, c)];
+          const int thr = (cur[jj] - score_q_any(plan, i, rdi, sm.kmer, k8[t], bins[t], cls_stride, jj)) - plan.thr_pred[i];
+          for (int base = 0; base <= jj; base += 32) {
+            const int k = base + lane;
+            const bool pred = (k <= jj) && (prev[t][k] + Gq[jj - k] >= thr);
+            const unsigned bal = __ballot_sync(0xffffffffu, pred);
+            if (lane == 0 && bal) bitmap[base >> 5] |= bal;
+          }
+          __syncwarp();
+        }
+        for (int base = 0; base < P; base += 32) {
+          const unsigned word = bitmap[base >> 5];
+          if ((word >> lane) & 1u) {
+            const int idx = count[t] + __popc(word & lt_mask);
+            if (idx < CAP) cj[at(t, i - 1, idx)] = base + lane;
+          }
+          count[t] += __popc(word);
         }
         __syncwarp();
       }
-      for (int base = 0; base < P; base += 32) {
-        const unsigned word = bitmap[base >> 5];
-        const bool pred = (word >> lane) & 1u;
-        if (pred) {
-          const int idx = count + __popc(word & lt_mask);
-          if (idx < kCandCap) cj[(i - 1) * kCandCap + idx] = base + lane;
-        }
-        count += __popc(word);
-      }
     }
-    if (count > kCandCap) return false;
-    if (lane == 0) cn[i - 1] = count;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      if (count[t] > CAP) failed[t] = true;
+      if (lane == 0) cn[t * p.max_rec + i - 1] = min(count[t], CAP);
+    }
     __syncwarp();
   }
-  // (3) exact scores of all candidate cells (independent of the chain: one pass, lane = one candidate), then the
-  //     exact forward recurrence on the candidate sets
+
+  int okp[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) okp[t] = (active[t] && !failed[t]) ? 1 : 0;
+
+  // (3) exact scores of every candidate cell (they do not depend on the chain): lanes = (pair, stage) when every
+  //     list holds one cell, otherwise list by list
   {
-    int tot = 0;
-    for (int i = 0; i < n; ++i) tot += cn[i];
-    if (tot <= 32) {
-      int st = -1, idx = 0, acc = 0;
-      for (int i = 0; i < n; ++i) {
-        if (st < 0 && lane < acc + cn[i]) {
-          st = i;
-          idx = lane - acc;
-        }
-        acc += cn[i];
+    bool one_each = (NT * n <= 32);
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      if (!okp[t]) continue;
+      for (int i = 0; i < n; ++i) one_each = one_each && (cn[t * p.max_rec + i] == 1);
+    }
+    if (one_each) {
+      const int t = lane / n, i = lane - t * n;
+      if (t < NT && pick(okp, t)) {
+        const int slot = warp * NT + t;
+        cr[at(t, i, 0)] = score_exact_any(sm.rec[i], sm.pool, sm.seqw + (size_t)slot * f.seqw_stride,
+                                          p.bins + (size_t)pick(seq, t) * p.bins_row_stride, cls_stride, cj[at(t, i, 0)]);
       }
-      if (st >= 0) cr[st * kCandCap + idx] = score_exact_any(sm.rec[st], sm.pool, w, bins_seq, cls_stride, cj[st * kCandCap + idx]);
     } else {
-      for (int i = 0; i < n; ++i)
-        if (lane < cn[i]) cr[i * kCandCap + lane] = score_exact_any(sm.rec[i], sm.pool, w, bins_seq, cls_stride, cj[i * kCandCap + lane]);
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        if (!okp[t]) continue;
+        for (int i = 0; i < n; ++i)
+          if (lane < cn[t * p.max_rec + i]) cr[at(t, i, lane)] = score_exact_any(sm.rec[i], sm.pool, w[t], bins[t], cls_stride, cj[at(t, i, lane)]);
+      }
     }
   }
   __syncwarp();
-  if (lane < cn[0]) cv[lane] = cr[lane];
-  __syncwarp();
-  for (int i = 1; i < n; ++i) {
-    if (lane < cn[i]) {
-      const int j = cj[i * kCandCap + lane];
-      const double rj = cr[i * kCandCap + lane];
-      const double *G = sm.G + (size_t)(i - 1) * p.g_stride + kGPad;
-      double best = neg_inf();
-      int arg = -1;
-      const int np = cn[i - 1];
-      for (int d = 0; d < np; ++d) {  // ascending k: the first k that attains the maximum wins (organism.c:365)
-        const int k = cj[(i - 1) * kCandCap + d];
-        if (k <= j) {
-          const double cand = (cv[(i - 1) * kCandCap + d] + G[j - k]) + rj;
-          if (best < cand) {
-            best = cand;
-            arg = d;
+
+  // (4) exact forward recurrence on the candidate sets: lane = (pair, candidate), all pairs side by side
+  {
+    const int t = lane / CAP, c = lane - t * CAP;
+    const bool mine = (t < NT) && pick(okp, t);
+    if (mine && c < cn[t * p.max_rec]) cv[at(t, 0, c)] = cr[at(t, 0, c)];
+    __syncwarp();
+    for (int i = 1; i < n; ++i) {
+      if (mine && c < cn[t * p.max_rec + i]) {
+        const int j = cj[at(t, i, c)];
+        const double rj = cr[at(t, i, c)];
+        const double *G = sm.G + (size_t)(i - 1) * p.g_stride + kGPad;
+        double best = neg_inf();
+        int arg = -1;
+        const int np = cn[t * p.max_rec + i - 1];
+        for (int d = 0; d < np; ++d) {  // ascending k: the first k that attains the maximum wins (organism.c:365)
+          const int k = cj[at(t, i - 1, d)];
+          if (k <= j) {
+            const double cand = (cv[at(t, i - 1, d)] + G[j - k]) + rj;
+            if (best < cand) {
+              best = cand;
+              arg = d;
+            }
           }
         }
+        cv[at(t, i, c)] = best;
+        ca[at(t, i, c)] = arg;
       }
-      cv[i * kCandCap + lane] = best;
-      ca[i * kCandCap + lane] = arg;
+      __syncwarp();
     }
-    __syncwarp();
   }
-  // (4) first maximum of the last row (_aux.c:149-158) and traceback (organism.c:398-427)
-  if (lane == 0) {
+
+  // (5) first maximum of the last row (_aux.c:149-158) and traceback (organism.c:398-427): lane t serves pair t
+  if (lane < NT && pick(okp, lane)) {
+    const int t = lane;
     int c = 0;
-    const int cnt = cn[n - 1];
+    const int cnt = cn[t * p.max_rec + n - 1];
     for (int d = 1; d < cnt; ++d)
-      if (cv[(n - 1) * kCandCap + d] > cv[(n - 1) * kCandCap + c]) c = d;
-    const size_t pair = (size_t)v.o * p.n_seq_total + seq;
-    p.E[pair] = cv[(n - 1) * kCandCap + c];
+      if (cv[at(t, n - 1, d)] > cv[at(t, n - 1, c)]) c = d;
+    const size_t pair = (size_t)v.o * p.n_seq_total + pick(seq, t);
+    p.E[pair] = cv[at(t, n - 1, c)];
     if (f.want_trace) {
       for (int i = n - 1; i >= 1; --i) {
-        const int d = ca[i * kCandCap + c];
-        const int j = cj[i * kCandCap + c];
-        const int k = cj[(i - 1) * kCandCap + (d < 0 ? 0 : d)];
+        const int d = ca[at(t, i, c)];
+        const int j = cj[at(t, i, c)];
+        const int k = cj[at(t, i - 1, d < 0 ? 0 : d)];
         const int gap = d < 0 ? 0 : j - k;
-        p.rsc[pair * p.max_rec + i] = cr[i * kCandCap + c];
+        p.rsc[pair * p.max_rec + i] = cr[at(t, i, c)];
         p.csc[pair * p.max_rec + i - 1] = d < 0 ? 0.0 : sm.G[(size_t)(i - 1) * p.g_stride + kGPad + gap];
         p.gaps[pair * p.max_rec + i] = gap;
         c = d < 0 ? 0 : d;
       }
-      p.rsc[pair * p.max_rec] = cr[c];
-      p.gaps[pair * p.max_rec] = cj[c];
+      p.rsc[pair * p.max_rec] = cr[at(t, 0, c)];
+      p.gaps[pair * p.max_rec] = cj[at(t, 0, c)];
     }
   }
   __syncwarp();
-  return true;
 }
 
 // Adds the quantised scores of recognizer r to a row (or, for stage 0, writes them): row[j] (+)= Rq_r[j], j < P,
@@ -647,22 +741,25 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
       const unsigned hit = __ballot_sync(0xffffffffu, nan_hit);
       if ((hit >> (team * TEAM)) & ((TEAM == 32) ? 0xffffffffu : ((1u << TEAM) - 1u))) decline = true;
     }
-    // ---- phase 2: exact refinement, one pair after the other, whole warp ---------------------------------
-    for (int t = 0; t < NT; ++t) {
-      const int t_seq = __shfl_sync(0xffffffffu, seq, t * TEAM);
-      const int t_live = __shfl_sync(0xffffffffu, (int)live, t * TEAM);
-      const int t_decline = __shfl_sync(0xffffffffu, (int)decline, t * TEAM);
-      if (!t_live) continue;
-      bool done = false;
-      if (!t_decline) {
-        const int t_slot = warp * NT + t;
-        done = refine_pair(f, v, sm, sm.rowsq + (size_t)t_slot * f.slotq_stride,
-                           f.scratch + ((size_t)blockIdx.x * nwarps * NT + t_slot) * f.scratch_slot_stride,
-                           sm.seqw + (size_t)t_slot * f.seqw_stride, sm.k8 + (size_t)t_slot * f.k8_stride, t_seq, warp, lane);
+    // ---- phase 2: exact refinement of the warp's NT pairs, side by side ------------------------------------------
+    {
+      int r_seq[NT];
+      bool r_active[NT], r_failed[NT], r_live[NT];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        r_seq[t] = __shfl_sync(0xffffffffu, seq, t * TEAM);
+        r_live[t] = __shfl_sync(0xffffffffu, (int)live, t * TEAM) != 0;
+        r_active[t] = r_live[t] && !__shfl_sync(0xffffffffu, (int)decline, t * TEAM);
       }
-      if (!done && lane == 0) {
-        const int idx = atomicAdd(f.fb_count, 1);
-        if (idx < f.fb_cap) f.fb_pairs[idx] = make_int2(v.o, t_seq);
+      refine_round<NT>(f, v, sm, warp, lane, nwarps, r_seq, r_active, r_failed);
+      if (lane == 0) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          if (r_live[t] && (!r_active[t] || r_failed[t])) {
+            const int idx = atomicAdd(f.fb_count, 1);
+            if (idx < f.fb_cap) f.fb_pairs[idx] = make_int2(v.o, r_seq[t]);
+          }
+        }
       }
     }
     __syncwarp();
