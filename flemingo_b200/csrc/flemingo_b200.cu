@@ -888,7 +888,8 @@ extern "C" int fl_calculate(fl_ctx *ctx, const char *sequence, int seq_len, cons
   double energy = 0.0;
   std::vector<int> gaps(n_rec);
   std::vector<double> rsc(n_rec), csc(n_rec);
-  rc = place_batch(ctx, ctx->scratch_pop, set, &con_begin, FL_WANT_TRACE, &energy, gaps.data(), rsc.data(), csc.data());
+  rc = place_batch(ctx, ctx->scratch_pop, set, &con_begin, FL_WANT_TRACE | FL_EXACT_ONLY,  // one pair: the exact kernel alone is the shortest path
+                    &energy, gaps.data(), rsc.data(), csc.data());
   if (rc) return rc;
   for (int i = 0; i < n_rec; ++i) {
     rec_scores[i] = rsc[i];
