@@ -144,7 +144,7 @@ struct SeqSet {
   bool valid = false;
   int n_seq = 0;
   std::vector<SeqClass> classes;
-  DevBuf packed, unk, word_off, unk_off, order, has_unk, d_len, bins, raw, d_offsets;
+  DevBuf packed, unk, word_off, unk_off, order, has_unk, d_len, bins, raw, d_offsets, k8, k8_off;
   int max_len = 0;
   unsigned long long bins_signature = 0;  // shape-class signature the bins were computed for (0 = none)
   long long bins_row_stride = 0;
@@ -229,7 +229,7 @@ extern "C" int fl_ctx_destroy(fl_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (SeqSet &s : ctx->sets) {
-    s.packed.release(); s.unk.release(); s.word_off.release(); s.unk_off.release(); s.order.release(); s.has_unk.release(); s.d_len.release(); s.bins.release(); s.raw.release(); s.d_offsets.release(); s.E.release();
+    s.packed.release(); s.unk.release(); s.word_off.release(); s.unk_off.release(); s.order.release(); s.has_unk.release(); s.d_len.release(); s.bins.release(); s.raw.release(); s.d_offsets.release(); s.k8.release(); s.k8_off.release(); s.E.release();
   }
   release_pop(ctx->pop);
   release_pop(ctx->scratch_pop);
@@ -264,8 +264,8 @@ extern "C" int fl_sync(fl_ctx *ctx) {
 
 static int upload_sequences(fl_ctx *ctx, SeqSet &set, const char *bytes, const long long *offsets, int n_seq) {
   if (n_seq < 0 || (n_seq > 0 && (!bytes || !offsets))) return fail(FL_E_ARG, "fl_upload_sequences: bad arguments");
-  std::vector<int> len(n_seq), word_off(n_seq), unk_off(n_seq), order(n_seq);
-  long long words = 0, uwords = 0;
+  std::vector<int> len(n_seq), word_off(n_seq), unk_off(n_seq), order(n_seq), k8_off(n_seq);
+  long long words = 0, uwords = 0, k8_units = 0;
   bool one_length = true;
   for (int s = 0; s < n_seq; ++s) {
     const long long l = offsets[s + 1] - offsets[s];
@@ -273,9 +273,11 @@ static int upload_sequences(fl_ctx *ctx, SeqSet &set, const char *bytes, const l
     len[s] = (int)l;
     word_off[s] = (int)words;
     unk_off[s] = (int)uwords;
+    k8_off[s] = (int)k8_units;
     words += (l + 15) / 16;
     uwords += (l + 31) / 32;
-    if (words > 0x7fffffffLL) return fail(FL_E_ARG, "fl_upload_sequences: set too large");
+    k8_units += (l + kK8Pad + 15) / 16;
+    if (words > 0x7fffffffLL || k8_units > 0x7fffffffLL) return fail(FL_E_ARG, "fl_upload_sequences: set too large");
     order[s] = s;
     one_length = one_length && (len[s] == len[0]);
   }
@@ -293,7 +295,8 @@ static int upload_sequences(fl_ctx *ctx, SeqSet &set, const char *bytes, const l
       (rc = set.word_off.ensure((size_t)n_seq * 4 + 4)) || (rc = set.unk_off.ensure((size_t)n_seq * 4 + 4)) ||
       (rc = set.order.ensure((size_t)n_seq * 4 + 4)) || (rc = set.has_unk.ensure((size_t)n_seq + 4)) ||
       (rc = set.d_len.ensure((size_t)n_seq * 4 + 4)) || (rc = set.raw.ensure(raw_bytes + 16)) ||
-      (rc = set.d_offsets.ensure(((size_t)n_seq + 1) * 8)))
+      (rc = set.d_offsets.ensure(((size_t)n_seq + 1) * 8)) || (rc = set.k8.ensure((size_t)k8_units * 16 + 16)) ||
+      (rc = set.k8_off.ensure((size_t)n_seq * 4 + 4)))
     return rc;
   if (n_seq) {
     // raw bytes go up as they are; the 2-bit packing runs on the device (pack_sequences_kernel)
@@ -305,10 +308,12 @@ static int upload_sequences(fl_ctx *ctx, SeqSet &set, const char *bytes, const l
     CK(cudaMemcpyAsync(set.unk_off.p, unk_off.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(set.order.p, order.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(set.d_len.p, len.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(set.k8_off.p, k8_off.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, ctx->stream));
     pack_sequences_kernel<<<(unsigned)n_seq, 64, 0, ctx->stream>>>(set.raw.as<unsigned char>(), set.d_offsets.as<long long>(),
                                                                     set.word_off.as<int>(), set.unk_off.as<int>(),
                                                                     set.packed.as<unsigned>(), set.unk.as<unsigned>(),
-                                                                    set.has_unk.as<unsigned char>());
+                                                                    set.has_unk.as<unsigned char>(), set.k8_off.as<int>(),
+                                                                    set.k8.as<unsigned char>());
     CK(cudaGetLastError());
     ctx->launches++;
     CK(cudaStreamSynchronize(ctx->stream));  // the staging vectors die at return
@@ -571,6 +576,8 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
     pp.packed = set.packed.as<unsigned>();
     pp.unk = set.unk.as<unsigned>();
     pp.word_off = set.word_off.as<int>();
+    pp.k8g = set.k8.as<unsigned char>();
+    pp.k8_off = set.k8_off.as<int>();
     pp.unk_off = set.unk_off.as<int>();
     pp.order = set.order.as<int>();
     pp.class_begin = cl.begin;
@@ -609,9 +616,7 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
     const bool allow_fast = !(flags & FL_EXACT_ONLY);
     FastParams fp;
     fp.gq_stride = kGPad + Pmax + kGPad;
-    fp.seqw_stride = (cl.len + 15) / 16 + 3;
-    fp.k8_stride = (cl.len + 7) & ~3;  // 4-mer codes of positions 0..S+2 (a partial last group overshoots by <= 3)
-    fp.bitmap_words = (Pmax + 31) / 32 + 1;
+    fp.k8_stride = (cl.len + kK8Pad + 15) & ~15;  // the sequence's block of 4-mer codes, as laid out by pack_sequences_kernel
     fp.want_trace = trace ? 1 : 0;
     fp.has_unk = set.has_unk.as<unsigned char>();
     int kmer_cap = 0;
@@ -640,12 +645,14 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
       fast_rowq[j] = (Pmax + kFastConfigs[j].J + 3) & ~3;
       fast_slot[j] = ((2 * fast_rowq[j] + 31) & ~31) + (team & 31);
       int best_occ = 0;
-      static const int kWarpChoices[] = {16, 14, 12, 10, 8, 6, 4, 2, 1};
+      static const int kWarpChoices[] = {16, 14, 12, 10, 8, 7, 6, 4, 2, 1};
+      const char *force_w = getenv("FLEMINGO_FAST_WARPS");
       for (int nw : kWarpChoices) {
+        if (force_w && atoi(force_w) != nw) continue;
         const size_t d = (size_t)pp.pool_stride + (size_t)(P.max_rec - 1) * pp.g_stride + 2ull * nw * P.max_rec * kCandCap;
-        const size_t i = (size_t)(P.max_rec - 1) * fp.gq_stride + fp.kmer_cap + (size_t)nw * nt * fast_slot[j] + (size_t)nw * nt * fp.seqw_stride +
-                         2ull * nw * P.max_rec * kCandCap + (size_t)nw * nt * P.max_rec + (size_t)nw * fp.bitmap_words;
-        const size_t bytes = d * 8 + i * 4 + sizeof(RecDesc) * P.max_rec + sizeof(FastPlan) + 16 + (size_t)nw * nt * fp.k8_stride;
+        const size_t i = (size_t)(P.max_rec - 1) * fp.gq_stride + fp.kmer_cap + (size_t)nw * nt * fast_slot[j] +
+                         2ull * nw * P.max_rec * kCandCap + (size_t)nw * nt * P.max_rec;
+        const size_t bytes = d * 8 + i * 4 + sizeof(RecDesc) * P.max_rec + sizeof(FastPlan) + 48 + (size_t)nw * nt * fp.k8_stride;
         if (bytes > (size_t)kMaxSmem) continue;
         const int ctas = (int)std::min<size_t>(233472 / (bytes + 1024), 32);
         // ptxas settles at ~100 registers per thread for every tile size (launch bound 512 threads), which caps the
@@ -730,6 +737,9 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
         fp.n_items = (int)items;
         fp.work_counter = ctx->work_counters.as<int>() + (ctx->launches % 1024);
         CK(cudaMemsetAsync(fp.work_counter, 0, sizeof(int), ctx->stream));
+        if (getenv("FLEMINGO_DEBUG_LAUNCH"))
+          fprintf(stderr, "fast launch: cfg J=%d team=%d warps=%d ctas/sm=%d grid=%lld items=%lld spc=%d smem=%zu\n", kFastConfigs[j].J, team, nw,
+                  fast_ctas_per_sm[j], grid, items, spc, fast_smem[j]);
         kFastConfigs[j].fn<<<(unsigned)grid, nw * 32, fast_smem[j], ctx->stream>>>(fp);
         CK(cudaGetLastError());
         ctx->launches++;
@@ -774,6 +784,36 @@ extern "C" int fl_path_stats(fl_ctx *ctx, long long *fast_pairs, long long *fall
   unsigned long long fb = 0;
   CK(cudaMemcpyAsync(&fb, ctx->fb_total.p, sizeof fb, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+#ifdef FL_PHASE_CLOCKS
+  {
+    unsigned long long clk[16] = {0};
+    CK(cudaMemcpyFromSymbol(clk, g_phase_clk, sizeof clk));
+    static const char *names[16] = {"prologue", "plan", "unpack", "scores", "dp_stage", "refine(5)", "misc", "claim/tail", "refine(1)", "refine(2)", "refine(3)", "refine(4)", "", "", "", ""};
+    double tot = 0;
+    for (int i = 0; i < 12; ++i) tot += (double)clk[i];
+    fprintf(stderr, "stage scans: all-single %llu, mixed %llu, candidates %llu\n", clk[12], clk[13], clk[14]);
+    for (int i = 0; i < 12; ++i) fprintf(stderr, "phase %-10s %14llu ticks %5.1f %%\n", names[i], clk[i], tot > 0 ? 100.0 * clk[i] / tot : 0.0);
+    unsigned long long zero[16] = {0};
+    CK(cudaMemcpyToSymbol(g_phase_clk, zero, sizeof zero));
+    if (!getenv("FLEMINGO_TIMELINE")) {
+      int zc[16] = {0};
+      CK(cudaMemcpyToSymbol(g_timeline_n, zc, sizeof zc));
+      CK(cudaMemcpyToSymbol(g_timeline_slots, zc, sizeof(int)));
+    }
+    if (const char *path = getenv("FLEMINGO_TIMELINE")) {
+      std::vector<unsigned long long> tl(16 * kTimelineEvents);
+      int cnt[16];
+      CK(cudaMemcpyFromSymbol(tl.data(), g_timeline, tl.size() * 8));
+      CK(cudaMemcpyFromSymbol(cnt, g_timeline_n, sizeof cnt));
+
+      if (FILE *fh = fopen(path, "w")) {
+        for (int w = 0; w < 16; ++w)
+          for (int e = 0; e < cnt[w]; ++e) fprintf(fh, "%d %llu %d\n", w, tl[(size_t)w * kTimelineEvents + e] >> 4, (int)(tl[(size_t)w * kTimelineEvents + e] & 15));
+        fclose(fh);
+      }
+    }
+  }
+#endif
   if (fast_pairs) *fast_pairs = ctx->fast_pairs;
   if (fallback_pairs) *fallback_pairs = (long long)fb;
   ctx->fast_pairs = 0;

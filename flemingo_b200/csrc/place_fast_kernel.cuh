@@ -34,10 +34,8 @@ struct FastParams {
   int gq_stride;     // ints per quantised connector table (kGPad + Pmax + kGPad)
   int rowq_stride;   // ints per quantised row
   int slotq_stride;  // ints per pair slot (2 ping-pong rows), == TEAM (mod 32) so that teams hit disjoint banks
-  int seqw_stride;   // u32 words per packed sequence copy
-  int k8_stride;     // bytes per 4-mer code array (S + pad, multiple of 4)
+  int k8_stride;     // bytes per 4-mer code array (S + kK8Pad rounded up to 16)
   int kmer_cap;      // ints available for the 4-mer tables of one organism
-  int bitmap_words;  // u32 words of the per-warp candidate bitmap
   int want_trace;
   int *scratch;      // global rows 0..n-3 of every resident pair slot (only the last two rows stay in shared memory)
   long long scratch_slot_stride;  // ints per pair slot in `scratch` (max_rec * rowq_stride)
@@ -50,6 +48,9 @@ struct FastPlan {
   int sent;                              // sentinel ("minus infinity" of the integer pass)
   int ok;                                // 0: this organism cannot use the integer pass
   int item;                              // work item the CTA is processing (claimed by thread 0)
+#ifdef FL_PHASE_CLOCKS
+  int trace_base;                        // profiling build: first timeline row of this CTA, or -1
+#endif
   int thr_final;                         // slack on the last row
   int thr_pred[FL_MAX_RECOGNIZERS];      // slack on predecessor scans of stage i
   int ngroups[FL_MAX_RECOGNIZERS];       // 4-mer groups of PSSM recognizer i (0 for a shape recognizer)
@@ -60,7 +61,6 @@ struct FastPlan {
 struct FastSmem {
   double *pool, *G, *cv, *cr;
   int *Gq, *kmer, *rowsq, *cj, *ca, *cn;
-  unsigned *seqw, *bitmap;
   unsigned char *k8;
   RecDesc *rec;
   FastPlan *plan;
@@ -77,13 +77,11 @@ __device__ __forceinline__ FastSmem carve_fast(const FastParams &f, unsigned cha
   s.rec = reinterpret_cast<RecDesc *>(s.plan + 1);
   s.Gq = reinterpret_cast<int *>(s.rec + p.max_rec);
   s.kmer = s.Gq + (size_t)(p.max_rec - 1) * f.gq_stride;
-  s.rowsq = s.kmer + f.kmer_cap;
-  s.seqw = reinterpret_cast<unsigned *>(s.rowsq + (size_t)nwarps * nt * f.slotq_stride);
-  s.cj = reinterpret_cast<int *>(s.seqw + (size_t)nwarps * nt * f.seqw_stride);
+  s.rowsq = reinterpret_cast<int *>((reinterpret_cast<unsigned long long>(s.kmer + f.kmer_cap) + 15ull) & ~15ull);  // 16-byte rows: cp.async targets
+  s.cj = s.rowsq + (size_t)nwarps * nt * f.slotq_stride;
   s.ca = s.cj + (size_t)nwarps * p.max_rec * kCandCap;
   s.cn = s.ca + (size_t)nwarps * p.max_rec * kCandCap;
-  s.bitmap = reinterpret_cast<unsigned *>(s.cn + (size_t)nwarps * nt * p.max_rec);
-  s.k8 = reinterpret_cast<unsigned char *>(s.bitmap + (size_t)nwarps * f.bitmap_words);
+  s.k8 = reinterpret_cast<unsigned char *>((reinterpret_cast<unsigned long long>(s.cn + (size_t)nwarps * nt * p.max_rec) + 15ull) & ~15ull);
   return s;
 }
 
@@ -109,14 +107,6 @@ __device__ __forceinline__ int warp_max_i(int v) {
   return v;
 }
 
-// base code (0..3) at position pos of a packed copy (16 bases per word, LSB first)
-__device__ __forceinline__ int packed_code(const unsigned *w, int pos) { return (w[pos >> 4] >> (2 * (pos & 15))) & 3; }
-
-// 8-bit code of the 4-mer starting at position q of a packed copy
-__device__ __forceinline__ unsigned kmer_code(const unsigned *__restrict__ w, int q) {
-  return __funnelshift_r(w[q >> 4], w[(q >> 4) + 1], 2 * (q & 15)) & 0xffu;
-}
-
 // quantised PSSM score at `pos` (already including the recognizer's forward offset): one 4-mer lookup per group.
 // k8[q] = code of the 4-mer starting at q, built once per pair (the same codes serve every recognizer and group).
 __device__ __forceinline__ int score_q(const int *__restrict__ tab, int ngroups, const unsigned char *__restrict__ k8, int pos) {
@@ -126,11 +116,12 @@ __device__ __forceinline__ int score_q(const int *__restrict__ tab, int ngroups,
   return v;
 }
 
-// exact PSSM score (recognizer.c:130-168) from the packed copy; the fast path only sees ACGT sequences
-__device__ __forceinline__ double score_exact_packed(const RecDesc &r, const double *s_pool, const unsigned *w, int pos) {
+// exact PSSM score (recognizer.c:130-168); the base at position q is the low 2 bits of its 4-mer code, and the fast
+// path only sees ACGT sequences
+__device__ __forceinline__ double score_exact_k8(const RecDesc &r, const double *s_pool, const unsigned char *k8, int pos) {
   const double *m = s_pool + r.data;
   double s = 0.0;
-  for (int col = 0; col < r.len; ++col) s += m[4 * col + packed_code(w, pos + col)];
+  for (int col = 0; col < r.len; ++col) s += m[4 * col + (k8[pos + col] & 3)];
   return s;
 }
 
@@ -142,9 +133,9 @@ __device__ __forceinline__ int score_q_any(const FastPlan &plan, int r, const Re
   return kmer[plan.kmer_off[r] + bins_seq[(size_t)rd.cls * cls_stride + rd.fwd + j]];
 }
 // exact score of recognizer rd at relative offset j
-__device__ __forceinline__ double score_exact_any(const RecDesc &rd, const double *s_pool, const unsigned *w,
+__device__ __forceinline__ double score_exact_any(const RecDesc &rd, const double *s_pool, const unsigned char *k8,
                                                   const unsigned char *__restrict__ bins_seq, size_t cls_stride, int j) {
-  if (rd.kind == 0) return score_exact_packed(rd, s_pool, w, rd.fwd + j);
+  if (rd.kind == 0) return score_exact_k8(rd, s_pool, k8, rd.fwd + j);
   int dummy = 0;  // a NaN null model keeps the organism off this path (build_fast_plan), so nothing to flag here
   return score_shape_bin(rd, s_pool, bins_seq[(size_t)rd.cls * cls_stride + rd.fwd + j], dummy);
 }
@@ -338,27 +329,59 @@ __device__ void build_fast_plan(const FastParams &f, const OrgView &v, const Fas
 // pair index t so that the NT dependency chains (row maxima, warp votes, score chains) interleave, and the per-pair
 // scalar work (exact recurrence, outputs) runs on NT lanes at once instead of NT times on one lane.
 // Candidate lists hold kCandCap / NT cells per stage and pair; a pair that needs more is handed to the exact kernel.
-// Quantised row i of a pair: the last two stages are still in the shared ping-pong buffers, older ones in global scratch.
-__device__ __forceinline__ const int *row_q(const FastParams &f, int n, int i, const int *rows_smem, const int *rows_glob) {
-  return (i >= n - 2) ? rows_smem + (size_t)(i & 1) * f.rowq_stride : rows_glob + (size_t)i * f.rowq_stride;
+// Quantised row i of a pair lives in the shared ping-pong buffer (i & 1): rows n-1 and n-2 are still there after the
+// forward pass, older rows are streamed back from global scratch (cp.async) one stage ahead of the scan that needs them.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+#ifdef FL_PHASE_CLOCKS
+// profiling build only (tools/phase_clocks.sh): SM-clock ticks per phase, summed over the lane-0 threads of all warps
+__device__ unsigned long long g_phase_clk[16];
+// timeline of CTA 0: [warp][event] = (clock << 3) | phase that just ended
+constexpr int kTimelineEvents = 8192;
+__device__ unsigned long long g_timeline[16 * kTimelineEvents];
+__device__ int g_timeline_n[16];
+__device__ int g_timeline_slots;       // CTAs that arrived on the traced SM
+__device__ int g_timeline_sm = 0;
+#define PHASE_MARK(idx)                                                   \
+  do {                                                                    \
+    const long long now_ = clock64();                                     \
+    if (lane == 0) {                                                      \
+      atomicAdd(&g_phase_clk[idx], (unsigned long long)(now_ - phase_t0)); \
+      const int row_ = tl_base + warp;                                    \
+      if (tl_base >= 0 && row_ < 16 && g_timeline_n[row_] < kTimelineEvents) \
+        g_timeline[row_ * kTimelineEvents + g_timeline_n[row_]++] = ((unsigned long long)now_ << 4) | (idx); \
+    }                                                                     \
+    phase_t0 = clock64();                                                 \
+  } while (0)
+#define PHASE_ARG , long long &phase_t0, int tl_base
+#define PHASE_PASS , phase_t0, tl_base
+#else
+#define PHASE_MARK(idx) do { } while (0)
+#define PHASE_ARG
+#define PHASE_PASS
+#endif
 
 template <int NT>
 __device__ __forceinline__ void refine_round(const FastParams &f, const OrgView &v, const FastSmem &sm, int warp, int lane,
-                                             int nwarps, const int (&seq)[NT], const bool (&active)[NT], bool (&failed)[NT]) {
+                                             int nwarps, const int (&seq)[NT], const bool (&active)[NT], bool (&failed)[NT] PHASE_ARG) {
+  constexpr int TEAM = 32 / NT;
   constexpr int CAP = kCandCap / NT;
   constexpr int kLowest = -0x7fffffff - 1;
+  constexpr int kNone = 0x7fffffff;
   const PlaceParams &p = f.base;
   const FastPlan &plan = *sm.plan;
   const int n = v.n, P = v.P;
+  const int tl = lane % TEAM, team = lane / TEAM;
   // per-warp candidate storage, indexed [t][stage][c]
   int *cj = sm.cj + (size_t)warp * p.max_rec * kCandCap;
   int *ca = sm.ca + (size_t)warp * p.max_rec * kCandCap;
   int *cn = sm.cn + (size_t)warp * NT * p.max_rec;
   double *cv = sm.cv + (size_t)warp * p.max_rec * kCandCap;
   double *cr = sm.cr + (size_t)warp * p.max_rec * kCandCap;
-  unsigned *bitmap = sm.bitmap + (size_t)warp * f.bitmap_words;
-  const unsigned lt_mask = (1u << lane) - 1u;
   const size_t cls_stride = (size_t)p.n_seq_total * p.bins_row_stride;
   auto at = [&](int t, int i, int c) { return (t * p.max_rec + i) * CAP + c; };
   // value of a small per-pair register array at a lane-dependent pair index (select chain, no local memory)
@@ -369,166 +392,151 @@ __device__ __forceinline__ void refine_round(const FastParams &f, const OrgView 
     return r;
   };
 
-  const int *rows[NT];
-  const int *rowg[NT];
-  const unsigned *w[NT];
-  const unsigned char *k8[NT];
+  const unsigned char *k8s[NT];
   const unsigned char *bins[NT];
 #pragma unroll
   for (int t = 0; t < NT; ++t) {
-    const int slot = warp * NT + t;
-    rows[t] = sm.rowsq + (size_t)slot * f.slotq_stride;
-    rowg[t] = f.scratch + ((size_t)blockIdx.x * nwarps * NT + slot) * f.scratch_slot_stride;
-    w[t] = sm.seqw + (size_t)slot * f.seqw_stride;
-    k8[t] = sm.k8 + (size_t)slot * f.k8_stride;
+    k8s[t] = sm.k8 + (size_t)(warp * NT + t) * f.k8_stride;
     bins[t] = p.bins + (size_t)seq[t] * p.bins_row_stride;
-    failed[t] = false;
   }
+  // Stages (1) and (2) run team-parallel: the TEAM lanes of a pair scan that pair's rows, the NT pairs of the warp
+  // side by side in the same instructions.
+  const int slot = warp * NT + team;
+  int *my_rows = sm.rowsq + (size_t)slot * f.slotq_stride;
+  const int *my_rowg = f.scratch + ((size_t)blockIdx.x * nwarps * NT + slot) * f.scratch_slot_stride;
+  const unsigned char *my_k8 = sm.k8 + (size_t)slot * f.k8_stride;
+  int my_seq = seq[0];
+  bool my_active = active[0];
+#pragma unroll
+  for (int t = 1; t < NT; ++t) {
+    my_seq = (team == t) ? seq[t] : my_seq;
+    my_active = (team == t) ? active[t] : my_active;
+  }
+  const unsigned char *my_bins = p.bins + (size_t)my_seq * p.bins_row_stride;
+  bool my_failed = false;
+  auto row_s = [&](int i) { return my_rows + (size_t)(i & 1) * f.rowq_stride; };
+  // streams row i (<= n-3) of the team's pair from global scratch into its ping-pong buffer; the caller makes sure
+  // the buffer's previous content (row i+2) is dead and waits (cp_async_wait_all + __syncwarp) before reading
+  const int row_chunks = (P + 3) >> 2;
+  auto prefetch_row = [&](int i) {
+    int *dst = row_s(i);
+    const int *src = my_rowg + (size_t)i * f.rowq_stride;
+    for (int c = tl; c < row_chunks; c += TEAM) cp_async16(dst + 4 * c, src + 4 * c);
+  };
+  // Appends the cells flagged in `m` (bit b of lane tl = cell k0 + TEAM*b + tl) to the candidate list of stage i in
+  // ascending order; `count` is the team's running total (lists are capped, the total keeps counting).
+  auto emit = [&](unsigned m, int k0, int i, int &count) {
+    for (;;) {
+      const int mine = m ? k0 + TEAM * (__ffs(m) - 1) + tl : kNone;
+      int best = mine;
+#pragma unroll
+      for (int o = TEAM >> 1; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+      if (!__any_sync(0xffffffffu, best != kNone)) break;
+      if (best != kNone) {
+        if (mine == best) {
+          m &= m - 1;
+          if (count < CAP) cj[at(team, i, count)] = best;
+        }
+        ++count;
+        if (count > CAP) m = 0;  // the pair is handed back anyway: stop enumerating a massive tie
+      }
+    }
+  };
 
-  // (1) candidates on the last row: maxima of the NT rows in one sweep, then one compaction sweep
+  // (1) candidates on the last row: every offset within thr_final of the row maximum
   {
-    const int *row[NT];
-    int mx[NT], thr[NT], count[NT];
+    const int *row = row_s(n - 1);
+    int mx = kLowest;
+#pragma unroll 4
+    for (int j = tl; j < P; j += TEAM) mx = max(mx, row[j]);
 #pragma unroll
-    for (int t = 0; t < NT; ++t) {
-      row[t] = row_q(f, n, n - 1, rows[t], rowg[t]);
-      mx[t] = kLowest;
-      count[t] = 0;
-    }
-#pragma unroll 2
-    for (int j = lane; j < P; j += 32) {
+    for (int o = TEAM >> 1; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const int thr = mx - plan.thr_final;
+    int count = 0;
+    for (int k0 = 0; k0 < P; k0 += 32 * TEAM) {
+      unsigned m = 0;
 #pragma unroll
-      for (int t = 0; t < NT; ++t) mx[t] = max(mx[t], row[t][j]);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int t = 0; t < NT; ++t) mx[t] = max(mx[t], __shfl_xor_sync(0xffffffffu, mx[t], o));
-    }
-#pragma unroll
-    for (int t = 0; t < NT; ++t) thr[t] = mx[t] - plan.thr_final;
-    for (int base = 0; base < P; base += 64) {
-      int x[NT][2];
-#pragma unroll
-      for (int t = 0; t < NT; ++t) {
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int j = base + 32 * u + lane;
-          x[t][u] = (j < P) ? row[t][j] : kLowest;
-        }
+      for (int b = 0; b < 32; ++b) {
+        const int k = k0 + TEAM * b + tl;
+        if (k0 + TEAM * b >= P) break;
+        if (k < P && row[k] >= thr) m |= 1u << b;
       }
-#pragma unroll
-      for (int t = 0; t < NT; ++t) {
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const bool pred = x[t][u] >= thr[t];
-          const unsigned bal = __ballot_sync(0xffffffffu, pred);
-          if (pred) {
-            const int idx = count[t] + __popc(bal & lt_mask);
-            if (idx < CAP) cj[at(t, n - 1, idx)] = base + 32 * u + lane;
-          }
-          count[t] += __popc(bal);
-        }
-      }
+      emit(my_active ? m : 0u, k0, n - 1, count);
     }
-#pragma unroll
-    for (int t = 0; t < NT; ++t) {
-      if (count[t] > CAP) failed[t] = true;
-      if (lane == 0) cn[t * p.max_rec + n - 1] = min(count[t], CAP);
-    }
+    if (count > CAP) my_failed = true;
+    if (tl == 0) cn[team * p.max_rec + n - 1] = min(count, CAP);
   }
   __syncwarp();
+  PHASE_MARK(8);
 
-  // (2) candidate sets of the earlier stages, top down
-  const int words = (P + 31) >> 5;
+  // (2) candidate sets of the earlier stages, top down: union over the stage's candidates j of the predecessors k
+  //     with Cq_{i-1}[k] + Gq[j-k] within thr_pred of (Cq_i[j] - Rq_i[j])
   for (int i = n - 1; i >= 1; --i) {
     const int *Gq = sm.Gq + (size_t)(i - 1) * f.gq_stride + kGPad;
     const RecDesc rdi = sm.rec[i];
-    const int *prev[NT];
-    int cnt[NT], count[NT];
-    bool all_single = true;
-#pragma unroll
-    for (int t = 0; t < NT; ++t) {
-      prev[t] = row_q(f, n, i - 1, rows[t], rowg[t]);
-      cnt[t] = (active[t] && !failed[t]) ? cn[t * p.max_rec + i] : 0;
-      count[t] = 0;
-      all_single = all_single && (cnt[t] <= 1);
+    if (i - 1 <= n - 3) {  // row i-1 was requested during the previous stage
+      cp_async_wait_all();
+      __syncwarp();
     }
-    if (all_single) {
-      // the usual case: at most one candidate per pair; the NT predecessor scans run side by side
-      int j[NT], thr[NT], jmax = -1;
+    const int *prev = row_s(i - 1);
+    const int *cur = row_s(i);
+    const int cnt = (my_active && !my_failed) ? cn[team * p.max_rec + i] : 0;
+    int cmax = cnt, jj[CAP], thr[CAP], jmax = -1;
 #pragma unroll
-      for (int t = 0; t < NT; ++t) {
-        j[t] = cnt[t] ? cj[at(t, i, 0)] : -1;
-        const int *cur = row_q(f, n, i, rows[t], rowg[t]);
-        thr[t] = cnt[t] ? (cur[j[t]] - score_q_any(plan, i, rdi, sm.kmer, k8[t], bins[t], cls_stride, j[t])) - plan.thr_pred[i] : 0;
-        jmax = max(jmax, j[t]);
-      }
-      for (int base = 0; base <= jmax; base += 64) {
-        int x[NT][2];
+    for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
 #pragma unroll
-        for (int t = 0; t < NT; ++t) {
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int k = base + 32 * u + lane;
-            x[t][u] = (k <= j[t]) ? prev[t][k] + Gq[j[t] - k] : kLowest;
-          }
-        }
-#pragma unroll
-        for (int t = 0; t < NT; ++t) {
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const bool pred = (x[t][u] >= thr[t]) && (base + 32 * u + lane <= j[t]);
-            const unsigned bal = __ballot_sync(0xffffffffu, pred);
-            if (pred) {
-              const int idx = count[t] + __popc(bal & lt_mask);
-              if (idx < CAP) cj[at(t, i - 1, idx)] = base + 32 * u + lane;
-            }
-            count[t] += __popc(bal);
-          }
-        }
-      }
-    } else {
-      // several candidates somewhere: pair by pair, union of the predecessor sets through a bitmap (sorted, no duplicates)
-#pragma unroll
-      for (int t = 0; t < NT; ++t) {
-        if (cnt[t] == 0) continue;
-        const int *cur = row_q(f, n, i, rows[t], rowg[t]);
-        for (int q = lane; q < words; q += 32) bitmap[q] = 0u;
-        __syncwarp();
-        for (int c = 0; c < cnt[t]; ++c) {
-          const int jj = cj[at(t, i, c)];
-          const int thr = (cur[jj] - score_q_any(plan, i, rdi, sm.kmer, k8[t], bins[t], cls_stride, jj)) - plan.thr_pred[i];
-          for (int base = 0; base <= jj; base += 32) {
-            const int k = base + lane;
-            const bool pred = (k <= jj) && (prev[t][k] + Gq[jj - k] >= thr);
-            const unsigned bal = __ballot_sync(0xffffffffu, pred);
-            if (lane == 0 && bal) bitmap[base >> 5] |= bal;
-          }
-          __syncwarp();
-        }
-        for (int base = 0; base < P; base += 32) {
-          const unsigned word = bitmap[base >> 5];
-          if ((word >> lane) & 1u) {
-            const int idx = count[t] + __popc(word & lt_mask);
-            if (idx < CAP) cj[at(t, i - 1, idx)] = base + lane;
-          }
-          count[t] += __popc(word);
-        }
-        __syncwarp();
+    for (int c = 0; c < CAP; ++c) {
+      jj[c] = -1;
+      thr[c] = 0;
+      if (c < cmax && c < cnt) {
+        jj[c] = cj[at(team, i, c)];
+        thr[c] = (cur[jj[c]] - score_q_any(plan, i, rdi, sm.kmer, my_k8, my_bins, cls_stride, jj[c])) - plan.thr_pred[i];
+        jmax = max(jmax, jj[c]);
       }
     }
 #pragma unroll
-    for (int t = 0; t < NT; ++t) {
-      if (count[t] > CAP) failed[t] = true;
-      if (lane == 0) cn[t * p.max_rec + i - 1] = min(count[t], CAP);
+    for (int o = 16; o > 0; o >>= 1) jmax = max(jmax, __shfl_xor_sync(0xffffffffu, jmax, o));
+    if (i >= 2) {  // row i is dead from here on: its buffer receives row i-2 while row i-1 is scanned
+      __syncwarp();
+      prefetch_row(i - 2);
     }
+    int count = 0;
+    for (int k0 = 0; k0 <= jmax; k0 += 32 * TEAM) {
+      unsigned m = 0;
+      if (cmax <= 1) {
+        // the usual case: one candidate per pair
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+          const int k = k0 + TEAM * b + tl;
+          if (k0 + TEAM * b > jmax) break;
+          if (k <= jj[0] && prev[k] + Gq[jj[0] - k] >= thr[0]) m |= 1u << b;
+        }
+      } else {
+        for (int b = 0; b < 32; ++b) {
+          const int k = k0 + TEAM * b + tl;
+          if (k0 + TEAM * b > jmax) break;
+          if (k <= jmax) {
+            const int pv = prev[k];
+            bool hit = false;
+#pragma unroll
+            for (int c = 0; c < CAP; ++c) hit = hit || (k <= jj[c] && pv + Gq[jj[c] - k] >= thr[c]);
+            if (hit) m |= 1u << b;
+          }
+        }
+      }
+      emit(m, k0, i - 1, count);
+    }
+    if (count > CAP) my_failed = true;
+    if (tl == 0) cn[team * p.max_rec + i - 1] = min(count, CAP);
     __syncwarp();
   }
+#pragma unroll
+  for (int t = 0; t < NT; ++t) failed[t] = __shfl_sync(0xffffffffu, (int)my_failed, t * TEAM) != 0;
 
   int okp[NT];
 #pragma unroll
   for (int t = 0; t < NT; ++t) okp[t] = (active[t] && !failed[t]) ? 1 : 0;
+  PHASE_MARK(9);
 
   // (3) exact scores of every candidate cell (they do not depend on the chain): lanes = (pair, stage) when every
   //     list holds one cell, otherwise list by list
@@ -543,7 +551,7 @@ __device__ __forceinline__ void refine_round(const FastParams &f, const OrgView 
       const int t = lane / n, i = lane - t * n;
       if (t < NT && pick(okp, t)) {
         const int slot = warp * NT + t;
-        cr[at(t, i, 0)] = score_exact_any(sm.rec[i], sm.pool, sm.seqw + (size_t)slot * f.seqw_stride,
+        cr[at(t, i, 0)] = score_exact_any(sm.rec[i], sm.pool, sm.k8 + (size_t)slot * f.k8_stride,
                                           p.bins + (size_t)pick(seq, t) * p.bins_row_stride, cls_stride, cj[at(t, i, 0)]);
       }
     } else {
@@ -551,11 +559,12 @@ __device__ __forceinline__ void refine_round(const FastParams &f, const OrgView 
       for (int t = 0; t < NT; ++t) {
         if (!okp[t]) continue;
         for (int i = 0; i < n; ++i)
-          if (lane < cn[t * p.max_rec + i]) cr[at(t, i, lane)] = score_exact_any(sm.rec[i], sm.pool, w[t], bins[t], cls_stride, cj[at(t, i, lane)]);
+          if (lane < cn[t * p.max_rec + i]) cr[at(t, i, lane)] = score_exact_any(sm.rec[i], sm.pool, k8s[t], bins[t], cls_stride, cj[at(t, i, lane)]);
       }
     }
   }
   __syncwarp();
+  PHASE_MARK(10);
 
   // (4) exact forward recurrence on the candidate sets: lane = (pair, candidate), all pairs side by side
   {
@@ -588,6 +597,7 @@ __device__ __forceinline__ void refine_round(const FastParams &f, const OrgView 
     }
   }
 
+  PHASE_MARK(11);
   // (5) first maximum of the last row (_aux.c:149-158) and traceback (organism.c:398-427): lane t serves pair t
   if (lane < NT && pick(okp, lane)) {
     const int t = lane;
@@ -673,6 +683,7 @@ __device__ __forceinline__ void add_scores_q(const FastPlan &plan, int r, const 
 // The fast kernel.  CTA = one organism x a chunk of sequences; a warp holds 32/TEAM pairs at a time, each
 // placed by a team of TEAM lanes with J x J register tiles of DPX cells.
 // ------------------------------------------------------------------------------------------------
+
 template <int J, int TEAM>
 __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
   constexpr int NT = 32 / TEAM;
@@ -683,8 +694,20 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
   const FastSmem sm = carve_fast(f, smem_raw, nwarps, NT);
   // persistent CTAs: work items (organism x chunk of sequences) are claimed from a device-side counter, so the
   // global row scratch is sized by the resident CTAs, not by the number of items, and the tail balances itself
+#ifdef FL_PHASE_CLOCKS
+  // the CTAs resident on one SM share the 16 timeline rows (rows = arrival order x warps per CTA)
+  if (threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    sm.plan->trace_base = ((int)smid == g_timeline_sm) ? atomicAdd(&g_timeline_slots, 1) * nwarps : -1;
+  }
+  __syncthreads();
+  const int tl_base = sm.plan->trace_base;
+  long long phase_t0 = clock64();
+#endif
   for (;;) {
   __syncthreads();
+  PHASE_MARK(7);
   if (threadIdx.x == 0) sm.plan->item = atomicAdd(f.work_counter, 1);
   __syncthreads();
   const int item = sm.plan->item;
@@ -693,16 +716,16 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
   const int chunk = item - oi * p.chunks;
   const OrgView v = organism_prologue(p, p.org_list[oi], sm.pool, sm.G, sm.rec);
   __syncthreads();
+  PHASE_MARK(0);
   if (warp == 0) build_fast_plan(f, v, sm, lane);
   __syncthreads();
+  PHASE_MARK(1);
   const FastPlan &plan = *sm.plan;
   const int n = v.n, P = v.P;
   const int slot = warp * NT + team;
   int *rowsq = sm.rowsq + (size_t)slot * f.slotq_stride;
   int *rowsg = f.scratch + ((size_t)blockIdx.x * nwarps * NT + slot) * f.scratch_slot_stride;
-  unsigned *w = sm.seqw + (size_t)slot * f.seqw_stride;
   unsigned char *k8 = sm.k8 + (size_t)slot * f.k8_stride;
-  const int nwords = (p.S + 15) >> 4;
 
   const int first = chunk * p.seqs_per_cta;
   const int last = min(p.class_count, first + p.seqs_per_cta);
@@ -715,25 +738,34 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
     bool nan_hit = false;
     // ---- phase 1: integer pass ---------------------------------------------------------------------
     if (plan.ok) {
-      const unsigned *pw = p.packed + p.word_off[seq];
-      for (int t = tl; t < f.seqw_stride; t += TEAM) w[t] = (t < nwords) ? __ldg(pw + t) : 0u;
+      {  // the sequence's 4-mer codes, precomputed at upload: one 16-byte cp.async per chunk
+        const unsigned char *src = p.k8g + 16ull * (unsigned long long)p.k8_off[seq];
+        for (int c = tl; c < (f.k8_stride >> 4); c += TEAM) cp_async16(k8 + 16 * c, src + 16 * c);
+        cp_async_wait_all();
+      }
       __syncwarp();
-      for (int q = tl; q < f.k8_stride; q += TEAM) k8[q] = (unsigned char)kmer_code(w, q);
-      __syncwarp();
+      PHASE_MARK(2);
       const unsigned char *bins_seq = p.bins + (size_t)seq * p.bins_row_stride;
       const size_t cls_stride = (size_t)p.n_seq_total * p.bins_row_stride;
       add_scores_q<J, TEAM, true>(plan, 0, sm.rec[0], sm.kmer, k8, bins_seq, cls_stride, rowsq, (0 <= n - 3) ? rowsg : nullptr, P, tl,
                                   nan_hit);
       __syncwarp();
+      PHASE_MARK(3);
       for (int i = 1; i < n; ++i) {
         const int *prev = rowsq + (size_t)((i - 1) & 1) * f.rowq_stride;
         int *cur = rowsq + (size_t)(i & 1) * f.rowq_stride;
         const int *Gq = sm.Gq + (size_t)(i - 1) * f.gq_stride + kGPad;
+#ifdef FL_SKIP_DP       // profiling only: marginal cost of the DP stages (results are wrong)
+        for (int j = tl; j < P; j += TEAM) cur[j] = prev[j] + Gq[j & 15];
+#else
         dp_stage<J, TEAM, OpI32>(prev, cur, Gq, P, tl, plan.sent);
+#endif
         __syncwarp();
+        PHASE_MARK(4);
         add_scores_q<J, TEAM, false>(plan, i, sm.rec[i], sm.kmer, k8, bins_seq, cls_stride, cur,
                                      (i <= n - 3) ? rowsg + (size_t)i * f.rowq_stride : nullptr, P, tl, nan_hit);
         __syncwarp();
+        PHASE_MARK(3);
       }
     }
     // a selected NaN-null bin: the pair goes to the exact kernel, which raises the reference's error
@@ -751,7 +783,15 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
         r_live[t] = __shfl_sync(0xffffffffu, (int)live, t * TEAM) != 0;
         r_active[t] = r_live[t] && !__shfl_sync(0xffffffffu, (int)decline, t * TEAM);
       }
-      refine_round<NT>(f, v, sm, warp, lane, nwarps, r_seq, r_active, r_failed);
+      PHASE_MARK(6);
+#ifdef FL_SKIP_REFINE   // profiling only: marginal cost of the refinement (results are wrong)
+      if (lane < NT && r_live[lane % NT]) p.E[(size_t)v.o * p.n_seq_total + seq] = (double)rowsq[(size_t)((n - 1) & 1) * f.rowq_stride + P - 1];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) r_failed[t] = false;
+#else
+      refine_round<NT>(f, v, sm, warp, lane, nwarps, r_seq, r_active, r_failed PHASE_PASS);
+#endif
+      PHASE_MARK(5);
       if (lane == 0) {
 #pragma unroll
         for (int t = 0; t < NT; ++t) {

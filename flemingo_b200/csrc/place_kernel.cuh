@@ -62,6 +62,8 @@ struct PlaceParams {
   const int *word_off;
   const int *unk_off;
   const int *order;
+  const unsigned char *k8g;  // 4-mer codes of every sequence (pack_sequences_kernel); sequence s starts at 16 * k8_off[s]
+  const int *k8_off;
   int class_begin, class_count, S, n_seq_total;
   // data tables and precomputed shape bins (shape_bins_kernel.cuh)
   const double *tables;

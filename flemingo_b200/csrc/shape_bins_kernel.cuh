@@ -97,10 +97,13 @@ __device__ __forceinline__ unsigned base_code_dev(unsigned char c) {
   }
 }
 
+constexpr int kK8Pad = 48;  // bytes of 4-mer codes kept past the end of a sequence (>= kMaxJ + longest group overshoot)
+
 __global__ void __launch_bounds__(64) pack_sequences_kernel(const unsigned char *__restrict__ raw, const long long *__restrict__ offsets,
                                                             const int *__restrict__ word_off, const int *__restrict__ unk_off,
                                                             unsigned *__restrict__ packed, unsigned *__restrict__ unk,
-                                                            unsigned char *__restrict__ has_unk) {
+                                                            unsigned char *__restrict__ has_unk, const int *__restrict__ k8_off,
+                                                            unsigned char *__restrict__ k8) {
   const int seq = blockIdx.x;
   const unsigned char *b = raw + offsets[seq];
   const int len = (int)(offsets[seq + 1] - offsets[seq]);
@@ -125,4 +128,17 @@ __global__ void __launch_bounds__(64) pack_sequences_kernel(const unsigned char 
   }
   any = __syncthreads_or(any);
   if (threadIdx.x == 0) has_unk[seq] = any ? 1 : 0;
+  // 4-mer codes for the integer pass of place_fast_kernel: k8[q] = sum_t code(b[q+t]) << 2t (0 past the end and for
+  // unknown bytes: sequences with unknown bytes never take that path), padded so that tiles may overshoot
+  unsigned char *kq = k8 + 16ull * (unsigned long long)k8_off[seq];
+  const int klen = (len + kK8Pad + 15) & ~15;
+  for (int q = threadIdx.x; q < klen; q += blockDim.x) {
+    unsigned code = 0u;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const unsigned c = (q + t < len) ? base_code_dev(b[q + t]) : 0u;
+      code |= (c & 3u) * (c < 4u) << (2 * t);
+    }
+    kq[q] = (unsigned char)code;
+  }
 }
