@@ -56,6 +56,8 @@ struct FastPlan {
   int ngroups[FL_MAX_RECOGNIZERS];       // 4-mer groups of PSSM recognizer i (0 for a shape recognizer)
   int kmer_off[FL_MAX_RECOGNIZERS];      // offset of its tables in s_kmer (4-mer tables, or nb-1 quantised bin scores)
   int err_half[FL_MAX_RECOGNIZERS];      // rounded table entries on a path through recognizer i (half units of error)
+  int unit_begin[FL_MAX_RECOGNIZERS];    // first quantisation work unit (table) of recognizer i
+  int units;                             // tables of all recognizers (the connectors follow)
 };
 
 struct FastSmem {
@@ -140,187 +142,214 @@ __device__ __forceinline__ double score_exact_any(const RecDesc &rd, const doubl
   return score_shape_bin(rd, s_pool, bins_seq[(size_t)rd.cls * cls_stride + rd.fwd + j], dummy);
 }
 
-// ---- quantisation plan of one organism (executed by warp 0 after the exact tables are in shared memory) ----
-__device__ void build_fast_plan(const FastParams &f, const OrgView &v, const FastSmem &sm, int lane) {
+// ---- quantisation plan of one organism (all threads of the CTA, after the exact tables are in shared memory) ----
+// Step A (warp 0) finds the value ranges and the scale; step B builds the quantised tables, one warp per table
+// (a 4-mer group of a PSSM, the bin table of a shape recognizer, a connector); step C (warp 0) adds up the integer
+// ranges, places the sentinel and the thresholds; step D fills the sentinel pads.  Contains block barriers.
+__device__ void build_fast_plan(const FastParams &f, const OrgView &v, const FastSmem &sm, int warp, int lane, int nwarps) {
   const PlaceParams &p = f.base;
   FastPlan *plan = sm.plan;
   const int n = v.n, P = v.P;
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
-  // (1) value ranges in doubles
-  double lo_sum = 0.0, hi_sum = 0.0, range = 0.0, g_lo_min = 0.0;
-  int kmer_need = 0;
-  bool bad = false;  // NaN anywhere in the tables
-  for (int r = 0; r < n; ++r) {
-    const RecDesc rd = sm.rec[r];
-    const double *m = sm.pool + rd.data;
-    double lo = 0.0, hi = 0.0;
-    if (rd.kind == 0) {
-      for (int c = lane; c < rd.len; c += 32) {
-        lo += fmin(fmin(m[4 * c], m[4 * c + 1]), fmin(m[4 * c + 2], m[4 * c + 3]));
-        hi += fmax(fmax(m[4 * c], m[4 * c + 1]), fmax(m[4 * c + 2], m[4 * c + 3]));
-        bad |= (m[4 * c] != m[4 * c]) | (m[4 * c + 1] != m[4 * c + 1]) | (m[4 * c + 2] != m[4 * c + 2]) | (m[4 * c + 3] != m[4 * c + 3]);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        lo += __shfl_xor_sync(0xffffffffu, lo, o);
-        hi += __shfl_xor_sync(0xffffffffu, hi, o);
-      }
-      kmer_need += 256 * ((rd.len + 3) >> 2);
-    } else {
-      // shape: alt[b] - null[b] over all bins (the bin actually selected varies per offset)
-      lo = inf;
-      hi = -inf;
-      // A NaN null bin (an empty bin of the null histogram) is never selected by a real k-mer; if it ever is, the
-      // reference exits.  Such bins are left out of the range and carry a marker that sends the pair to the exact
-      // kernel, which reports the error.
-      for (int b = lane; b < rd.nb - 1; b += 32) {
-        double x = m[(rd.nb - 1) + b] - m[b];
-        bad |= (m[(rd.nb - 1) + b] != m[(rd.nb - 1) + b]);
-        if (x != x) continue;
-        if (x < BIG_NEG) x = BIG_NEG;
-        lo = fmin(lo, x);
-        hi = fmax(hi, x);
-      }
-      lo = warp_min(lo);
-      hi = warp_max(hi);
-      if (!(lo <= hi)) bad = true;  // every bin is NaN
-      kmer_need += rd.nb - 1;
-    }
-    lo_sum += lo;
-    hi_sum += hi;
-    range += hi - lo;
-  }
-  for (int c = 0; c < n - 1; ++c) {
-    const double *Gc = sm.G + (size_t)c * p.g_stride + kGPad;
-    double lo = inf, hi = -inf;
-    for (int g = lane; g <= P - 2; g += 32) {  // legit gaps; g = P-1 is the reference's -1e10 sentinel
-      const double x = Gc[g];
-      lo = fmin(lo, x);
-      hi = fmax(hi, x);
-      bad |= (x != x);
-    }
-    lo = warp_min(lo);
-    hi = warp_max(hi);
-    lo_sum += lo;
-    hi_sum += hi;
-    range += hi - lo;
-    g_lo_min = fmin(g_lo_min, lo);
-  }
-  bad = __any_sync(0xffffffffu, bad);
-  // (2) scale: everything, including (n-1) sentinels of size ~range, must stay inside +-2^30
-  // the sentinel sits below the lowest legit gap energy by more than the whole value range (see below), and up
-  // to n-1 of them can add up on a (never selected) path
-  const double need = fabs(lo_sum) + fabs(hi_sum) + (double)n * (range + fabs(g_lo_min) + 2.0) + 2.0;
-  int ok = !bad && (P >= 2) && (need == need) && (need < 1.0e9) && (kmer_need <= f.kmer_cap);
-  int e = 0;
-  if (ok) {
-    e = ilogb(1073741824.0 / need) - 1;
-    if (e > 40) e = 40;
-    if (e < 0) ok = 0;
-  }
-  const double s = ok ? scalbn(1.0, e) : 1.0;
-  // (3) quantised tables, their integer ranges, thresholds
-  long long lo_q = 0, hi_q = 0, lo_q_rec = 0;
-  int groups_total = 0, off = 0, g_lo_q = 0;
-  if (ok) {
+  // per-table integer ranges of step B: red[2u], red[2u+1] = lo, hi of unit u (the candidate lists are idle now)
+  int *red = sm.cj;
+  const int red_cap = 2 * nwarps * p.max_rec * kCandCap;  // cj and ca are contiguous
+  if (warp == 0) {
+    // (A1) value ranges in doubles
+    double lo_sum = 0.0, hi_sum = 0.0, range = 0.0, g_lo_min = 0.0;
+    int kmer_need = 0, units = 0;
+    bool bad = false;  // NaN anywhere in the tables
     for (int r = 0; r < n; ++r) {
       const RecDesc rd = sm.rec[r];
       const double *m = sm.pool + rd.data;
-      if (rd.kind != 0) {
-        if (lane == 0) {
-          plan->ngroups[r] = 0;
-          plan->kmer_off[r] = off;
-          plan->err_half[r] = 1;
+      double lo = 0.0, hi = 0.0;
+      if (rd.kind == 0) {
+        for (int c = lane; c < rd.len; c += 32) {
+          lo += fmin(fmin(m[4 * c], m[4 * c + 1]), fmin(m[4 * c + 2], m[4 * c + 3]));
+          hi += fmax(fmax(m[4 * c], m[4 * c + 1]), fmax(m[4 * c + 2], m[4 * c + 3]));
+          bad |= (m[4 * c] != m[4 * c]) | (m[4 * c + 1] != m[4 * c + 1]) | (m[4 * c + 2] != m[4 * c + 2]) | (m[4 * c + 3] != m[4 * c + 3]);
         }
-        int lo = 0x7fffffff, hi = -0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          lo += __shfl_xor_sync(0xffffffffu, lo, o);
+          hi += __shfl_xor_sync(0xffffffffu, hi, o);
+        }
+        const int ng = (rd.len + 3) >> 2;
+        if (lane == 0) {
+          plan->ngroups[r] = ng;
+          plan->kmer_off[r] = kmer_need;
+          plan->err_half[r] = ng;
+          plan->unit_begin[r] = units;
+        }
+        kmer_need += 256 * ng;
+        units += ng;
+      } else {
+        // shape: alt[b] - null[b] over all bins (the bin actually selected varies per offset)
+        lo = inf;
+        hi = -inf;
+        // A NaN null bin (an empty bin of the null histogram) is never selected by a real k-mer; if it ever is, the
+        // reference exits.  Such bins are left out of the range and carry a marker that sends the pair to the exact
+        // kernel, which reports the error.
         for (int b = lane; b < rd.nb - 1; b += 32) {
           double x = m[(rd.nb - 1) + b] - m[b];
-          if (x != x) {
-            sm.kmer[off + b] = kNanBinMarker;
-            continue;
-          }
+          bad |= (m[(rd.nb - 1) + b] != m[(rd.nb - 1) + b]);
+          if (x != x) continue;
           if (x < BIG_NEG) x = BIG_NEG;
-          const int q = __double2int_rn(x * s);
-          sm.kmer[off + b] = q;
-          lo = min(lo, q);
-          hi = max(hi, q);
+          lo = fmin(lo, x);
+          hi = fmax(hi, x);
         }
-        lo_q += warp_min_i(lo);
-        hi_q += warp_max_i(hi);
-        off += rd.nb - 1;
-        groups_total += 1;
-        continue;
-      }
-      const int ng = (rd.len + 3) >> 2;
-      if (lane == 0) {
-        plan->ngroups[r] = ng;
-        plan->kmer_off[r] = off;
-        plan->err_half[r] = ng;
-      }
-      for (int g = 0; g < ng; ++g) {
-        int lo = 0x7fffffff, hi = -0x7fffffff;
-        for (int kmer = lane; kmer < 256; kmer += 32) {
-          double acc = 0.0;
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int col = 4 * g + t;
-            if (col < rd.len) acc += m[4 * col + ((kmer >> (2 * t)) & 3)];
-          }
-          const int q = __double2int_rn(acc * s);
-          sm.kmer[off + 256 * g + kmer] = q;
-          lo = min(lo, q);
-          hi = max(hi, q);
+        lo = warp_min(lo);
+        hi = warp_max(hi);
+        if (!(lo <= hi)) bad = true;  // every bin is NaN
+        if (lane == 0) {
+          plan->ngroups[r] = 0;
+          plan->kmer_off[r] = kmer_need;
+          plan->err_half[r] = 1;
+          plan->unit_begin[r] = units;
         }
-        lo_q += warp_min_i(lo);
-        hi_q += warp_max_i(hi);
+        kmer_need += rd.nb - 1;
+        units += 1;
       }
-      off += 256 * ng;
-      groups_total += ng;
+      lo_sum += lo;
+      hi_sum += hi;
+      range += hi - lo;
     }
-    lo_q_rec = lo_q;
     for (int c = 0; c < n - 1; ++c) {
       const double *Gc = sm.G + (size_t)c * p.g_stride + kGPad;
-      int *Gq = sm.Gq + (size_t)c * f.gq_stride + kGPad;
+      double lo = inf, hi = -inf;
+      for (int g = lane; g <= P - 2; g += 32) {  // legit gaps; g = P-1 is the reference's -1e10 sentinel
+        const double x = Gc[g];
+        lo = fmin(lo, x);
+        hi = fmax(hi, x);
+        bad |= (x != x);
+      }
+      lo = warp_min(lo);
+      hi = warp_max(hi);
+      lo_sum += lo;
+      hi_sum += hi;
+      range += hi - lo;
+      g_lo_min = fmin(g_lo_min, lo);
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    // (A2) scale: everything, including (n-1) sentinels of size ~range, must stay inside +-2^30
+    // the sentinel sits below the lowest legit gap energy by more than the whole value range (see below), and up
+    // to n-1 of them can add up on a (never selected) path
+    const double need = fabs(lo_sum) + fabs(hi_sum) + (double)n * (range + fabs(g_lo_min) + 2.0) + 2.0;
+    int ok = !bad && (P >= 2) && (need == need) && (need < 1.0e9) && (kmer_need <= f.kmer_cap) && (2 * (units + n - 1) <= red_cap);
+    int e = 0;
+    if (ok) {
+      e = ilogb(1073741824.0 / need) - 1;
+      if (e > 40) e = 40;
+      if (e < 0) ok = 0;
+    }
+    if (lane == 0) {
+      plan->scale = ok ? scalbn(1.0, e) : 1.0;
+      plan->ok = ok;
+      plan->units = units;
+    }
+  }
+  __syncthreads();
+  // (B) quantised tables and their integer ranges, one warp per table
+  const double s = plan->scale;
+  const int units = plan->units;
+  if (plan->ok) {
+    for (int u = warp; u < units + (n - 1); u += nwarps) {
       int lo = 0x7fffffff, hi = -0x7fffffff;
-      for (int g = lane; g <= P - 2; g += 32) {
-        const int q = __double2int_rn(Gc[g] * s);
-        Gq[g] = q;
-        lo = min(lo, q);
-        hi = max(hi, q);
+      if (u < units) {
+        int r = 0;
+        while (r + 1 < n && plan->unit_begin[r + 1] <= u) ++r;
+        const RecDesc rd = sm.rec[r];
+        const double *m = sm.pool + rd.data;
+        const int off = plan->kmer_off[r];
+        if (rd.kind != 0) {
+          for (int b = lane; b < rd.nb - 1; b += 32) {
+            double x = m[(rd.nb - 1) + b] - m[b];
+            if (x != x) {
+              sm.kmer[off + b] = kNanBinMarker;
+              continue;
+            }
+            if (x < BIG_NEG) x = BIG_NEG;
+            const int q = __double2int_rn(x * s);
+            sm.kmer[off + b] = q;
+            lo = min(lo, q);
+            hi = max(hi, q);
+          }
+        } else {
+          const int g = u - plan->unit_begin[r];
+          for (int kmer = lane; kmer < 256; kmer += 32) {
+            double acc = 0.0;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int col = 4 * g + t;
+              if (col < rd.len) acc += m[4 * col + ((kmer >> (2 * t)) & 3)];
+            }
+            const int q = __double2int_rn(acc * s);
+            sm.kmer[off + 256 * g + kmer] = q;
+            lo = min(lo, q);
+            hi = max(hi, q);
+          }
+        }
+      } else {
+        const int c = u - units;
+        const double *Gc = sm.G + (size_t)c * p.g_stride + kGPad;
+        int *Gq = sm.Gq + (size_t)c * f.gq_stride + kGPad;
+        for (int g = lane; g <= P - 2; g += 32) {
+          const int q = __double2int_rn(Gc[g] * s);
+          Gq[g] = q;
+          lo = min(lo, q);
+          hi = max(hi, q);
+        }
       }
       lo = warp_min_i(lo);
-      lo_q += lo;
-      hi_q += warp_max_i(hi);
-      g_lo_q = min(g_lo_q, lo);
-    }
-  }
-  const long long range_q = hi_q - lo_q;
-  const int thr_max = groups_total + n + 2 * kSlackUnits + 2;
-  // sentinel: below the lowest legit gap energy by more than (range of any path) + (largest threshold), so a path
-  // through it is below EVERY legit path of the same stage by more than any threshold
-  const long long sent = (long long)g_lo_q - (range_q + thr_max + 4);
-  if (ok && (lo_q_rec + (long long)(n - 1) * sent < -2000000000LL || hi_q > 2000000000LL || lo_q < -2000000000LL)) ok = 0;
-  if (ok) {
-    for (int c = 0; c < n - 1; ++c) {
-      int *Gq = sm.Gq + (size_t)c * f.gq_stride;
-      for (int i = lane; i < f.gq_stride; i += 32) {
-        const int g = i - kGPad;
-        if (!(g >= 0 && g <= P - 2)) Gq[i] = (int)sent;
+      hi = warp_max_i(hi);
+      if (lane == 0) {
+        red[2 * u] = lo;
+        red[2 * u + 1] = hi;
       }
     }
   }
-  if (lane == 0) {
-    plan->scale = s;
-    plan->sent = (int)sent;
-    plan->ok = ok;
-    // err_i (in half units) = groups of recognizers 0..i + i connectors
-    int half_units = 0;
-    for (int i = 0; i < n; ++i) {
-      // predecessors of stage i: values Cq_{i-1}[k] + Gq  ->  err_{i-1} + 0.5
-      plan->thr_pred[i] = half_units + 1 + 2 * kSlackUnits;   // 2 * (err_{i-1} + 0.5) = half_units + 1   (i >= 1)
-      half_units += plan->err_half[i] + (i > 0 ? 1 : 0);
+  __syncthreads();
+  // (C) integer ranges, sentinel, thresholds
+  if (warp == 0) {
+    int ok = plan->ok;
+    long long lo_q = 0, hi_q = 0, lo_q_rec = 0;
+    int g_lo_q = 0;
+    if (ok) {
+      for (int u = 0; u < units + (n - 1); ++u) {
+        if (u == units) lo_q_rec = lo_q;
+        lo_q += red[2 * u];
+        hi_q += red[2 * u + 1];
+        if (u >= units) g_lo_q = min(g_lo_q, red[2 * u]);
+      }
+      if (n == 1) lo_q_rec = lo_q;
     }
-    plan->thr_final = half_units + 2 * kSlackUnits;          // 2 * err_{n-1}
+    const long long range_q = hi_q - lo_q;
+    const int thr_max = units + n + 2 * kSlackUnits + 2;
+    // sentinel: below the lowest legit gap energy by more than (range of any path) + (largest threshold), so a path
+    // through it is below EVERY legit path of the same stage by more than any threshold
+    const long long sent = (long long)g_lo_q - (range_q + thr_max + 4);
+    if (ok && (lo_q_rec + (long long)(n - 1) * sent < -2000000000LL || hi_q > 2000000000LL || lo_q < -2000000000LL)) ok = 0;
+    if (lane == 0) {
+      plan->sent = (int)sent;
+      plan->ok = ok;
+      // err_i (in half units) = groups of recognizers 0..i + i connectors
+      int half_units = 0;
+      for (int i = 0; i < n; ++i) {
+        // predecessors of stage i: values Cq_{i-1}[k] + Gq  ->  err_{i-1} + 0.5
+        plan->thr_pred[i] = half_units + 1 + 2 * kSlackUnits;   // 2 * (err_{i-1} + 0.5) = half_units + 1   (i >= 1)
+        half_units += plan->err_half[i] + (i > 0 ? 1 : 0);
+      }
+      plan->thr_final = half_units + 2 * kSlackUnits;          // 2 * err_{n-1}
+    }
+  }
+  __syncthreads();
+  // (D) sentinel pads of the connector tables
+  if (plan->ok) {
+    const int sent = plan->sent;
+    for (int i = threadIdx.x; i < (n - 1) * f.gq_stride; i += blockDim.x) {
+      const int g = i % f.gq_stride - kGPad;
+      if (!(g >= 0 && g <= P - 2)) sm.Gq[i] = sent;
+    }
   }
 }
 
@@ -367,7 +396,7 @@ __device__ int g_timeline_sm = 0;
 
 template <int NT>
 __device__ __forceinline__ void refine_round(const FastParams &f, const OrgView &v, const FastSmem &sm, int warp, int lane,
-                                             int nwarps, const int (&seq)[NT], const bool (&active)[NT], bool (&failed)[NT] PHASE_ARG) {
+                                             int nwarps, const int (&seq)[NT], const bool (&active)[NT], bool (&failed)[NT], int part_max PHASE_ARG) {
   constexpr int TEAM = 32 / NT;
   constexpr int CAP = kCandCap / NT;
   constexpr int kLowest = -0x7fffffff - 1;
@@ -446,21 +475,22 @@ __device__ __forceinline__ void refine_round(const FastParams &f, const OrgView 
   // (1) candidates on the last row: every offset within thr_final of the row maximum
   {
     const int *row = row_s(n - 1);
-    int mx = kLowest;
-#pragma unroll 4
-    for (int j = tl; j < P; j += TEAM) mx = max(mx, row[j]);
+    int mx = part_max;  // the last score pass kept every lane's share of the row maximum
 #pragma unroll
     for (int o = TEAM >> 1; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     const int thr = mx - plan.thr_final;
     int count = 0;
     for (int k0 = 0; k0 < P; k0 += 32 * TEAM) {
-      unsigned m = 0;
+      // predicated, fully unrolled: the 32 loads are independent and go out back to back
+      int x[32];
 #pragma unroll
       for (int b = 0; b < 32; ++b) {
         const int k = k0 + TEAM * b + tl;
-        if (k0 + TEAM * b >= P) break;
-        if (k < P && row[k] >= thr) m |= 1u << b;
+        x[b] = (k < P) ? row[k] : kLowest;
       }
+      unsigned m = 0;
+#pragma unroll
+      for (int b = 0; b < 32; ++b) m |= (x[b] >= thr ? 1u : 0u) << b;
       emit(my_active ? m : 0u, k0, n - 1, count);
     }
     if (count > CAP) my_failed = true;
@@ -504,12 +534,17 @@ __device__ __forceinline__ void refine_round(const FastParams &f, const OrgView 
     for (int k0 = 0; k0 <= jmax; k0 += 32 * TEAM) {
       unsigned m = 0;
       if (cmax <= 1) {
-        // the usual case: one candidate per pair
+        // the usual case: one candidate per pair; predicated and unrolled in chunks of 8 independent load pairs
+        const int j0 = jj[0];
+        for (int b0 = 0; b0 < 32 && k0 + TEAM * b0 <= jmax; b0 += 8) {
+          int x[8];
 #pragma unroll
-        for (int b = 0; b < 32; ++b) {
-          const int k = k0 + TEAM * b + tl;
-          if (k0 + TEAM * b > jmax) break;
-          if (k <= jj[0] && prev[k] + Gq[jj[0] - k] >= thr[0]) m |= 1u << b;
+          for (int b = 0; b < 8; ++b) {
+            const int k = k0 + TEAM * (b0 + b) + tl;
+            x[b] = (k <= j0) ? prev[k] + Gq[j0 - k] : kLowest;
+          }
+#pragma unroll
+          for (int b = 0; b < 8; ++b) m |= (x[b] >= thr[0] ? 1u : 0u) << (b0 + b);
         }
       } else {
         for (int b = 0; b < 32; ++b) {
@@ -628,9 +663,11 @@ __device__ __forceinline__ void refine_round(const FastParams &f, const OrgView 
 // Adds the quantised scores of recognizer r to a row (or, for stage 0, writes them): row[j] (+)= Rq_r[j], j < P,
 // zeroes the J padding entries behind the row, and mirrors the finished row to global scratch when a later
 // refinement needs it.  The recognizer kind and the number of 4-mer groups are hoisted out of the offset loop.
+// Returns the largest value this lane wrote (the refinement of the last stage starts from the row maximum).
 template <int NG, int TEAM, bool FIRST>
-__device__ __forceinline__ void add_pssm_scores_q(const int *__restrict__ tab, int ng, const unsigned char *__restrict__ k,
-                                                  int *__restrict__ row, int *__restrict__ glob, int P, int tl) {
+__device__ __forceinline__ int add_pssm_scores_q(const int *__restrict__ tab, int ng, const unsigned char *__restrict__ k,
+                                                 int *__restrict__ row, int *__restrict__ glob, int P, int tl) {
+  int mx = -0x7fffffff - 1;
 #pragma unroll 4
   for (int j = tl; j < P; j += TEAM) {
     int v = FIRST ? 0 : row[j];
@@ -641,29 +678,32 @@ __device__ __forceinline__ void add_pssm_scores_q(const int *__restrict__ tab, i
       for (int g = 0; g < ng; ++g) v += tab[256 * g + k[j + 4 * g]];
     }
     row[j] = v;
+    mx = max(mx, v);
     if (glob) glob[j] = v;
   }
+  return mx;
 }
 
 template <int J, int TEAM, bool FIRST>
 __device__ __forceinline__ void add_scores_q(const FastPlan &plan, int r, const RecDesc &rd, const int *__restrict__ kmer,
                                              const unsigned char *__restrict__ k8, const unsigned char *__restrict__ bins_seq,
                                              size_t cls_stride, int *__restrict__ row, int *__restrict__ glob, int P, int tl,
-                                             bool &nan_hit) {
+                                             bool &nan_hit, int &row_max) {
   if (rd.kind == 0) {
     const int *tab = kmer + plan.kmer_off[r];
     const unsigned char *k = k8 + rd.fwd;
     const int ng = plan.ngroups[r];
     switch (ng) {
-      case 1: add_pssm_scores_q<1, TEAM, FIRST>(tab, ng, k, row, glob, P, tl); break;
-      case 2: add_pssm_scores_q<2, TEAM, FIRST>(tab, ng, k, row, glob, P, tl); break;
-      case 3: add_pssm_scores_q<3, TEAM, FIRST>(tab, ng, k, row, glob, P, tl); break;
-      case 4: add_pssm_scores_q<4, TEAM, FIRST>(tab, ng, k, row, glob, P, tl); break;
-      default: add_pssm_scores_q<0, TEAM, FIRST>(tab, ng, k, row, glob, P, tl); break;
+      case 1: row_max = add_pssm_scores_q<1, TEAM, FIRST>(tab, ng, k, row, glob, P, tl); break;
+      case 2: row_max = add_pssm_scores_q<2, TEAM, FIRST>(tab, ng, k, row, glob, P, tl); break;
+      case 3: row_max = add_pssm_scores_q<3, TEAM, FIRST>(tab, ng, k, row, glob, P, tl); break;
+      case 4: row_max = add_pssm_scores_q<4, TEAM, FIRST>(tab, ng, k, row, glob, P, tl); break;
+      default: row_max = add_pssm_scores_q<0, TEAM, FIRST>(tab, ng, k, row, glob, P, tl); break;
     }
   } else {
     const int *tab = kmer + plan.kmer_off[r];
     const unsigned char *b = bins_seq + (size_t)rd.cls * cls_stride + rd.fwd;
+    int mx = -0x7fffffff - 1;
 #pragma unroll 4
     for (int j = tl; j < P; j += TEAM) {
       int x = tab[b[j]];
@@ -673,8 +713,10 @@ __device__ __forceinline__ void add_scores_q(const FastPlan &plan, int r, const 
       }
       const int v = FIRST ? x : row[j] + x;
       row[j] = v;
+      mx = max(mx, v);
       if (glob) glob[j] = v;
     }
+    row_max = mx;
   }
   for (int t = tl; t < J; t += TEAM) row[P + t] = 0;  // padding behind the row: 0 + sentinel cannot wrap
 }
@@ -717,7 +759,7 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
   const OrgView v = organism_prologue(p, p.org_list[oi], sm.pool, sm.G, sm.rec);
   __syncthreads();
   PHASE_MARK(0);
-  if (warp == 0) build_fast_plan(f, v, sm, lane);
+  build_fast_plan(f, v, sm, warp, lane, nwarps);
   __syncthreads();
   PHASE_MARK(1);
   const FastPlan &plan = *sm.plan;
@@ -736,6 +778,7 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
     const int seq = p.order[p.class_begin + si];
     bool decline = !plan.ok || f.has_unk[seq];
     bool nan_hit = false;
+    int row_max = -0x7fffffff - 1;  // this lane's share of the maximum of the row written last
     // ---- phase 1: integer pass ---------------------------------------------------------------------
     if (plan.ok) {
       {  // the sequence's 4-mer codes, precomputed at upload: one 16-byte cp.async per chunk
@@ -748,7 +791,7 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
       const unsigned char *bins_seq = p.bins + (size_t)seq * p.bins_row_stride;
       const size_t cls_stride = (size_t)p.n_seq_total * p.bins_row_stride;
       add_scores_q<J, TEAM, true>(plan, 0, sm.rec[0], sm.kmer, k8, bins_seq, cls_stride, rowsq, (0 <= n - 3) ? rowsg : nullptr, P, tl,
-                                  nan_hit);
+                                  nan_hit, row_max);
       __syncwarp();
       PHASE_MARK(3);
       for (int i = 1; i < n; ++i) {
@@ -763,7 +806,7 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
         __syncwarp();
         PHASE_MARK(4);
         add_scores_q<J, TEAM, false>(plan, i, sm.rec[i], sm.kmer, k8, bins_seq, cls_stride, cur,
-                                     (i <= n - 3) ? rowsg + (size_t)i * f.rowq_stride : nullptr, P, tl, nan_hit);
+                                     (i <= n - 3) ? rowsg + (size_t)i * f.rowq_stride : nullptr, P, tl, nan_hit, row_max);
         __syncwarp();
         PHASE_MARK(3);
       }
@@ -789,7 +832,7 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
 #pragma unroll
       for (int t = 0; t < NT; ++t) r_failed[t] = false;
 #else
-      refine_round<NT>(f, v, sm, warp, lane, nwarps, r_seq, r_active, r_failed PHASE_PASS);
+      refine_round<NT>(f, v, sm, warp, lane, nwarps, r_seq, r_active, r_failed, row_max PHASE_PASS);
 #endif
       PHASE_MARK(5);
       if (lane == 0) {
