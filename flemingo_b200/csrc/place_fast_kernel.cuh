@@ -123,7 +123,14 @@ __device__ __forceinline__ int score_q(const int *__restrict__ tab, int ngroups,
 __device__ __forceinline__ double score_exact_k8(const RecDesc &r, const double *s_pool, const unsigned char *k8, int pos) {
   const double *m = s_pool + r.data;
   double s = 0.0;
-  for (int col = 0; col < r.len; ++col) s += m[4 * col + (k8[pos + col] & 3)];
+  for (int col = 0; col < r.len; col += 4) {  // loads four at a time, the adds stay in the reference's order
+    double a[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) a[t] = (col + t < r.len) ? m[4 * (col + t) + (k8[pos + col + t] & 3)] : 0.0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (col + t < r.len) s += a[t];
+  }
   return s;
 }
 
@@ -664,22 +671,43 @@ __device__ __forceinline__ void refine_round(const FastParams &f, const OrgView 
 // zeroes the J padding entries behind the row, and mirrors the finished row to global scratch when a later
 // refinement needs it.  The recognizer kind and the number of 4-mer groups are hoisted out of the offset loop.
 // Returns the largest value this lane wrote (the refinement of the last stage starts from the row maximum).
+// A lane handles four consecutive offsets at a time: the 4-mer codes arrive as aligned words (funnel-shifted by the
+// recognizer's byte offset), the row moves as int4.  Entries P..P+3 of the row's padding are written as zeros.
 template <int NG, int TEAM, bool FIRST>
-__device__ __forceinline__ int add_pssm_scores_q(const int *__restrict__ tab, int ng, const unsigned char *__restrict__ k,
+__device__ __forceinline__ int add_pssm_scores_q(const int *__restrict__ tab, int ng, const unsigned char *__restrict__ k8, int fwd,
                                                  int *__restrict__ row, int *__restrict__ glob, int P, int tl) {
-  int mx = -0x7fffffff - 1;
-#pragma unroll 4
-  for (int j = tl; j < P; j += TEAM) {
-    int v = FIRST ? 0 : row[j];
-    if (NG > 0) {
+  constexpr int kLow = -0x7fffffff - 1;
+  int mx = kLow;
+  const unsigned *kw = reinterpret_cast<const unsigned *>(k8 + (fwd & ~3));
+  const int sh = 8 * (fwd & 3);
+  const int groups = NG > 0 ? NG : ng;
+#pragma unroll 2
+  for (int j0 = 4 * tl; j0 < P; j0 += 4 * TEAM) {
+    int4 v = FIRST ? make_int4(0, 0, 0, 0) : *reinterpret_cast<const int4 *>(row + j0);
+    const unsigned *kp = kw + (j0 >> 2);
+    unsigned w0 = kp[0];
 #pragma unroll
-      for (int g = 0; g < NG; ++g) v += tab[256 * g + k[j + 4 * g]];
-    } else {
-      for (int g = 0; g < ng; ++g) v += tab[256 * g + k[j + 4 * g]];
+    for (int g = 0; g < groups; ++g) {
+      const unsigned w1 = kp[g + 1];
+      const unsigned c = __funnelshift_r(w0, w1, sh);  // codes of the 4-mers at fwd + j0 + 4g + {0,1,2,3}
+      const int *tg = tab + 256 * g;
+      v.x += tg[c & 0xffu];
+      v.y += tg[(c >> 8) & 0xffu];
+      v.z += tg[(c >> 16) & 0xffu];
+      v.w += tg[c >> 24];
+      w0 = w1;
     }
-    row[j] = v;
-    mx = max(mx, v);
-    if (glob) glob[j] = v;
+    if (j0 + 3 >= P) {
+      if (j0 + 1 >= P) v.y = 0;
+      if (j0 + 2 >= P) v.z = 0;
+      v.w = 0;
+    }
+    *reinterpret_cast<int4 *>(row + j0) = v;
+    if (glob) *reinterpret_cast<int4 *>(glob + j0) = v;
+    mx = max(mx, v.x);
+    mx = max(mx, (j0 + 1 < P) ? v.y : kLow);
+    mx = max(mx, (j0 + 2 < P) ? v.z : kLow);
+    mx = max(mx, (j0 + 3 < P) ? v.w : kLow);
   }
   return mx;
 }
@@ -691,30 +719,52 @@ __device__ __forceinline__ void add_scores_q(const FastPlan &plan, int r, const 
                                              bool &nan_hit, int &row_max) {
   if (rd.kind == 0) {
     const int *tab = kmer + plan.kmer_off[r];
-    const unsigned char *k = k8 + rd.fwd;
     const int ng = plan.ngroups[r];
     switch (ng) {
-      case 1: row_max = add_pssm_scores_q<1, TEAM, FIRST>(tab, ng, k, row, glob, P, tl); break;
-      case 2: row_max = add_pssm_scores_q<2, TEAM, FIRST>(tab, ng, k, row, glob, P, tl); break;
-      case 3: row_max = add_pssm_scores_q<3, TEAM, FIRST>(tab, ng, k, row, glob, P, tl); break;
-      case 4: row_max = add_pssm_scores_q<4, TEAM, FIRST>(tab, ng, k, row, glob, P, tl); break;
-      default: row_max = add_pssm_scores_q<0, TEAM, FIRST>(tab, ng, k, row, glob, P, tl); break;
+      case 1: row_max = add_pssm_scores_q<1, TEAM, FIRST>(tab, ng, k8, rd.fwd, row, glob, P, tl); break;
+      case 2: row_max = add_pssm_scores_q<2, TEAM, FIRST>(tab, ng, k8, rd.fwd, row, glob, P, tl); break;
+      case 3: row_max = add_pssm_scores_q<3, TEAM, FIRST>(tab, ng, k8, rd.fwd, row, glob, P, tl); break;
+      case 4: row_max = add_pssm_scores_q<4, TEAM, FIRST>(tab, ng, k8, rd.fwd, row, glob, P, tl); break;
+      default: row_max = add_pssm_scores_q<0, TEAM, FIRST>(tab, ng, k8, rd.fwd, row, glob, P, tl); break;
     }
   } else {
+    // shape recognizer: the precomputed bin of each offset (global, one byte per offset) indexes the quantised bin
+    // scores; four offsets per lane and iteration, bins fetched as aligned words like the 4-mer codes
     const int *tab = kmer + plan.kmer_off[r];
-    const unsigned char *b = bins_seq + (size_t)rd.cls * cls_stride + rd.fwd;
-    int mx = -0x7fffffff - 1;
-#pragma unroll 4
-    for (int j = tl; j < P; j += TEAM) {
-      int x = tab[b[j]];
-      if (x == kNanBinMarker) {
-        nan_hit = true;
-        x = 0;
+    const unsigned char *b = bins_seq + (size_t)rd.cls * cls_stride;
+    const unsigned *bw = reinterpret_cast<const unsigned *>(b + (rd.fwd & ~3));
+    const int sh = 8 * (rd.fwd & 3);
+    constexpr int kLow = -0x7fffffff - 1;
+    int mx = kLow;
+#pragma unroll 2
+    for (int j0 = 4 * tl; j0 < P; j0 += 4 * TEAM) {
+      const unsigned w0 = __ldg(bw + (j0 >> 2)), w1 = __ldg(bw + (j0 >> 2) + 1);
+      const unsigned c = __funnelshift_r(w0, w1, sh);
+      int4 v = FIRST ? make_int4(0, 0, 0, 0) : *reinterpret_cast<const int4 *>(row + j0);
+      int x[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        x[e] = (j0 + e < P) ? tab[(c >> (8 * e)) & 0xffu] : 0;
+        if (x[e] == kNanBinMarker) {
+          nan_hit = true;
+          x[e] = 0;
+        }
       }
-      const int v = FIRST ? x : row[j] + x;
-      row[j] = v;
-      mx = max(mx, v);
-      if (glob) glob[j] = v;
+      v.x += x[0];
+      v.y += x[1];
+      v.z += x[2];
+      v.w += x[3];
+      if (j0 + 3 >= P) {
+        if (j0 + 1 >= P) v.y = 0;
+        if (j0 + 2 >= P) v.z = 0;
+        v.w = 0;
+      }
+      *reinterpret_cast<int4 *>(row + j0) = v;
+      if (glob) *reinterpret_cast<int4 *>(glob + j0) = v;
+      mx = max(mx, v.x);
+      mx = max(mx, (j0 + 1 < P) ? v.y : kLow);
+      mx = max(mx, (j0 + 2 < P) ? v.z : kLow);
+      mx = max(mx, (j0 + 3 < P) ? v.w : kLow);
     }
     row_max = mx;
   }
