@@ -262,6 +262,19 @@ extern "C" int fl_sync(fl_ctx *ctx) {
   return check_device_errors(ctx);
 }
 
+// An asynchronous copy FROM PAGEABLE host memory returns only after the bytes have been staged for DMA, so the source
+// may be reused as soon as the call returns; a copy from pinned memory really is asynchronous.  Uploads therefore
+// synchronise only when a caller hands over pinned buffers.
+static bool is_pinned(const void *p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;  // unknown: be conservative
+  }
+  return a.type != cudaMemoryTypeUnregistered;
+}
+
 static int upload_sequences(fl_ctx *ctx, SeqSet &set, const char *bytes, const long long *offsets, int n_seq) {
   if (n_seq < 0 || (n_seq > 0 && (!bytes || !offsets))) return fail(FL_E_ARG, "fl_upload_sequences: bad arguments");
   std::vector<int> len(n_seq), word_off(n_seq), unk_off(n_seq), order(n_seq), k8_off(n_seq);
@@ -316,7 +329,7 @@ static int upload_sequences(fl_ctx *ctx, SeqSet &set, const char *bytes, const l
                                                                     set.k8.as<unsigned char>());
     CK(cudaGetLastError());
     ctx->launches++;
-    CK(cudaStreamSynchronize(ctx->stream));  // the staging vectors die at return
+    if (is_pinned(bytes)) CK(cudaStreamSynchronize(ctx->stream));  // the staging vectors are pageable (see is_pinned)
   }
   set.max_len = 0;
   for (int s2 = 0; s2 < n_seq; ++s2) set.max_len = std::max(set.max_len, len[s2]);
@@ -438,7 +451,6 @@ static int upload_population(fl_ctx *ctx, Population &P, const fl_population *po
       CK(cudaMemcpyAsync(P.d_cls_edges.p, pop->cls_edges, ncl * 8, cudaMemcpyHostToDevice, ctx->stream));
       CK(cudaMemcpyAsync(P.d_edges_pool.p, pop->edges_pool, (size_t)pop->n_edges * 8, cudaMemcpyHostToDevice, ctx->stream));
     }
-    CK(cudaStreamSynchronize(ctx->stream));
   }
   if ((rc = P.d_rec_begin.ensure((n_org + 1) * 4)) || (rc = P.d_rec_type.ensure(nr + 4)) || (rc = P.d_rec_len.ensure(nr * 4 + 4)) ||
       (rc = P.d_rec_nb.ensure(nr * 4 + 4)) || (rc = P.d_rec_data.ensure(nr * 8 + 8)) || (rc = P.d_pool_begin.ensure((n_org + 1) * 8)) ||
@@ -456,7 +468,9 @@ static int upload_population(fl_ctx *ctx, Population &P, const fl_population *po
   if (n_org) CK(cudaMemcpyAsync(P.d_con_M.p, pop->con_M, (size_t)n_org * 4, cudaMemcpyHostToDevice, st));
   if (pop->n_con) CK(cudaMemcpyAsync(P.d_con_pool.p, pop->con_pool, (size_t)pop->n_con * 8, cudaMemcpyHostToDevice, st));
   if (n_org) CK(cudaMemcpyAsync(P.d_sum_len.p, P.sum_len.data(), (size_t)n_org * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaStreamSynchronize(st));  // caller may free its arrays as soon as we return
+  // the caller may free its arrays as soon as we return
+  if (is_pinned(pop->con_pool) || is_pinned(pop->rec_pool) || is_pinned(pop->rec_begin) || is_pinned(pop->rec_data) || is_pinned(pop->edges_pool))
+    CK(cudaStreamSynchronize(st));
   P.valid = true;
   return FL_OK;
 }
@@ -723,7 +737,7 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
         const long long pairs = (long long)n_b * cl.count;
         const long long fast_target = (long long)n_sm * fast_ctas_per_sm[j] * 6;
         int spc = (int)std::max<long long>(per_round, (pairs + fast_target - 1) / fast_target);
-        spc = std::min(spc, std::max(per_round, 256));
+        spc = std::min(spc, std::max(per_round, getenv("FLEMINGO_FAST_SPC") ? atoi(getenv("FLEMINGO_FAST_SPC")) : 256));
         spc = ((spc + per_round - 1) / per_round) * per_round;
         fp.base = pp;
         fp.base.org_list = d_list + fast_begin[j];

@@ -123,14 +123,7 @@ __device__ __forceinline__ int score_q(const int *__restrict__ tab, int ngroups,
 __device__ __forceinline__ double score_exact_k8(const RecDesc &r, const double *s_pool, const unsigned char *k8, int pos) {
   const double *m = s_pool + r.data;
   double s = 0.0;
-  for (int col = 0; col < r.len; col += 4) {  // loads four at a time, the adds stay in the reference's order
-    double a[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) a[t] = (col + t < r.len) ? m[4 * (col + t) + (k8[pos + col + t] & 3)] : 0.0;
-#pragma unroll
-    for (int t = 0; t < 4; ++t)
-      if (col + t < r.len) s += a[t];
-  }
+  for (int col = 0; col < r.len; ++col) s += m[4 * col + (k8[pos + col] & 3)];
   return s;
 }
 

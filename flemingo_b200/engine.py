@@ -111,7 +111,7 @@ class Engine:
         blob = np.frombuffer(joined + b"\0", dtype=np.uint8)
         _cabi.check(self._lib.fl_upload_sequences(self._ctx, set_id, _ptr(blob), _ptr(offsets), len(seqs)))
         sset = SequenceSet(set_id=set_id, n_seq=len(seqs), lengths=lengths,
-                           class_len=sorted(set(int(x) for x in lengths)), sequences=list(sequences), blob=joined)
+                           class_len=[int(x) for x in np.unique(lengths)], sequences=list(sequences), blob=joined)
         self._sets[set_id] = sset
         return sset
 
@@ -194,9 +194,10 @@ class Engine:
     def evaluate(self, organisms, pos_sequences, neg_sequences, method: str = "Welch", gamma: float = 0.2,
                  reuse_sets: bool = True) -> np.ndarray:
         """One generation's fitness evaluation through host buffers: upload, place on both sets, reduce."""
-        self.upload_population(organisms)
+        # sequences first: their copies and the packing kernel run while the host packs the population
         pos = self.upload_sequences(pos_sequences, 0, reuse=reuse_sets)
         neg = self.upload_sequences(neg_sequences, 1, reuse=reuse_sets)
+        self.upload_population(organisms)
         self.place(pos, fetch=False)
         self.place(neg, fetch=False)
         return self.fitness(pos, neg, method, gamma)
