@@ -169,6 +169,7 @@ struct fl_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   DevBuf tables, err_flag, con_begin, org_list, gaps, rsc, csc, fit_out, fit_scratch, fb_count, fb_pairs, fast_scratch, fb_total, work_counters;
+  int fast_reg_warps[64] = {0};
   long long fast_pairs = 0, fallback_pairs = 0;  // statistics of the last fl_place_batch
   Population pop, scratch_pop;
   SeqSet sets[FL_MAX_SETS + 1];  // the extra slot serves fl_calculate
@@ -209,8 +210,14 @@ extern "C" int fl_ctx_create(int device, const double *tables, long long n_table
     CK(cudaFuncSetAttribute(kPlaceKernels[j][0], cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     CK(cudaFuncSetAttribute(kPlaceKernels[j][1], cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   }
-  for (int j = 0; j < kNumFastConfigs; ++j)
+  for (int j = 0; j < kNumFastConfigs; ++j) {
     CK(cudaFuncSetAttribute(kFastConfigs[j].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    // resident warps per SM the register file allows (64 K registers, allocated per warp in units of 8 per thread)
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, kFastConfigs[j].fn));
+    const int regs = std::max(8, (fa.numRegs + 7) & ~7);
+    ctx->fast_reg_warps[j] = std::max(1, 65536 / (regs * 32));
+  }
   CK(cudaFuncSetAttribute(place_list_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   CK(cudaFuncSetAttribute(place_list_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   *out = ctx;
@@ -669,9 +676,7 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
         const size_t bytes = d * 8 + i * 4 + sizeof(RecDesc) * P.max_rec + sizeof(FastPlan) + 48 + (size_t)nw * nt * fp.k8_stride;
         if (bytes > (size_t)kMaxSmem) continue;
         const int ctas = (int)std::min<size_t>(233472 / (bytes + 1024), 32);
-        // ptxas settles at ~100 registers per thread for every tile size (launch bound 512 threads), which caps the
-        // resident warps at 20 per SM
-        const int reg_warps = 20;
+        const int reg_warps = ctx->fast_reg_warps[j];  // 16-19 for the 101-124 registers ptxas settles at
         const int occ = std::min(ctas * nw, reg_warps);
         if (occ > best_occ) {
           best_occ = occ;

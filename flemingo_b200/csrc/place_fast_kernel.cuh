@@ -79,11 +79,15 @@ __device__ __forceinline__ FastSmem carve_fast(const FastParams &f, unsigned cha
   s.rec = reinterpret_cast<RecDesc *>(s.plan + 1);
   s.Gq = reinterpret_cast<int *>(s.rec + p.max_rec);
   s.kmer = s.Gq + (size_t)(p.max_rec - 1) * f.gq_stride;
-  s.rowsq = reinterpret_cast<int *>((reinterpret_cast<unsigned long long>(s.kmer + f.kmer_cap) + 15ull) & ~15ull);  // 16-byte rows: cp.async targets
+  // 16-byte aligned rows (cp.async / int4 targets).  Pointer + offset, not an integer round trip: the compiler must keep
+  // seeing a shared-memory pointer, or every row access of the DP loop turns into a generic load.
+  int *rows_unaligned = s.kmer + f.kmer_cap;
+  s.rowsq = rows_unaligned + (((16u - ((unsigned)__cvta_generic_to_shared(rows_unaligned) & 15u)) & 15u) >> 2);
   s.cj = s.rowsq + (size_t)nwarps * nt * f.slotq_stride;
   s.ca = s.cj + (size_t)nwarps * p.max_rec * kCandCap;
   s.cn = s.ca + (size_t)nwarps * p.max_rec * kCandCap;
-  s.k8 = reinterpret_cast<unsigned char *>((reinterpret_cast<unsigned long long>(s.cn + (size_t)nwarps * nt * p.max_rec) + 15ull) & ~15ull);
+  unsigned char *k8_unaligned = reinterpret_cast<unsigned char *>(s.cn + (size_t)nwarps * nt * p.max_rec);
+  s.k8 = k8_unaligned + ((16u - ((unsigned)__cvta_generic_to_shared(k8_unaligned) & 15u)) & 15u);
   return s;
 }
 
