@@ -88,12 +88,13 @@ constexpr int kNumFastConfigs = (int)(sizeof(kFastConfigs) / sizeof(kFastConfigs
 // Estimated issue slots per pair: tiles x (J*J cells + loads and bookkeeping), scaled by the share of the warp a team uses.
 static double fast_cost(int P, int J, int team) {
   const int NB = (P + J - 1) / J;
-  double tiles = 0;
+  double slots = 0;
   for (int r0 = 0; r0 < NB; r0 += 2 * team) {
     const int nbr = std::min(2 * team, NB - r0);
-    tiles += (2 * r0 + nbr + 2) & ~1;
+    const int iters = 2 * r0 + nbr + 1;  // dp_stage: iters - 1 full tiles, then one diagonal tile of J(J+1)/2 cells
+    slots += (iters - 1) * (J * J + 3.0 * J + 24.0) + (J * (J + 1) / 2 + 2.0 * J + 24.0);
   }
-  return tiles * (J * J + 3.0 * J + 24.0) * team / 32.0;
+  return slots * team / 32.0;
 }
 static int pick_fast(int P) {
   int best = 0;

@@ -161,14 +161,14 @@ struct TileState {
   int next_b; // row block of the second job, or -1
 };
 
+// Job bookkeeping shared by tile_step and tile_last: when the current job has walked all its k blocks, flush its J
+// rows, then start the folded partner block (or go idle) and load the first window of the new job into `A`.
 template <int J, class Op>
-__device__ __forceinline__ void tile_step(typename Op::T (&A)[J], typename Op::T (&B)[J], typename Op::T (&acc)[J],
-                                          TileState &st, const typename Op::T *__restrict__ prev,
-                                          typename Op::T *__restrict__ cur, const typename Op::T *__restrict__ G, int P,
-                                          typename Op::T lowest) {
+__device__ __forceinline__ void tile_switch(typename Op::T (&A)[J], typename Op::T (&acc)[J], TileState &st,
+                                            typename Op::T *__restrict__ cur, const typename Op::T *__restrict__ G,
+                                            typename Op::T lowest) {
   typedef typename Op::T T;
   if (st.kb == st.kend) {
-    // job finished: flush its rows, then start the folded partner block (or idle)
     // rows beyond P-1 of the last block land in the row's padding (the caller owns >= ceil(P/J)*J entries)
     typename Op::T *dst = cur + st.b * J;
 #pragma unroll
@@ -190,6 +190,15 @@ __device__ __forceinline__ void tile_step(typename Op::T (&A)[J], typename Op::T
       A[t] = ga[-t];
     }
   }
+}
+
+template <int J, class Op>
+__device__ __forceinline__ void tile_step(typename Op::T (&A)[J], typename Op::T (&B)[J], typename Op::T (&acc)[J],
+                                          TileState &st, const typename Op::T *__restrict__ prev,
+                                          typename Op::T *__restrict__ cur, const typename Op::T *__restrict__ G, int P,
+                                          typename Op::T lowest) {
+  typedef typename Op::T T;
+  tile_switch<J, Op>(A, acc, st, cur, G, lowest);
   // A[i] = G[c - i], B[i] = G[c - J - i] with c = (b - kb)*J + J-1: row t at step u needs G[(b-kb)*J + t - u]
   const T *gb = G + (st.b - st.kb) * J - 1;
   const T *pk = prev + st.kb * J;
@@ -206,6 +215,26 @@ __device__ __forceinline__ void tile_step(typename Op::T (&A)[J], typename Op::T
       const T g = (u <= t) ? A[J - 1 - t + u] : B[u - t - 1];
       acc[t] = Op::cell(acc[t], pv[u], g);
     }
+  }
+  st.kb += st.kstep;
+}
+
+// The LAST step of a round: every lane that still works is on the diagonal tile of its second job (kb == b), where
+// only the cells k <= j exist -- J(J+1)/2 of the J*J -- and only the `A` window is needed.
+template <int J, class Op>
+__device__ __forceinline__ void tile_last(typename Op::T (&A)[J], typename Op::T (&acc)[J], TileState &st,
+                                          const typename Op::T *__restrict__ prev, typename Op::T *__restrict__ cur,
+                                          const typename Op::T *__restrict__ G, typename Op::T lowest) {
+  typedef typename Op::T T;
+  tile_switch<J, Op>(A, acc, st, cur, G, lowest);
+  const T *pk = prev + st.kb * J;
+  T pv[J];
+#pragma unroll
+  for (int u = 0; u < J; ++u) pv[u] = pk[u];
+#pragma unroll
+  for (int u = 0; u < J; ++u) {
+#pragma unroll
+    for (int t = u; t < J; ++t) acc[t] = Op::cell(acc[t], pv[u], A[J - 1 - t + u]);
   }
   st.kb += st.kstep;
 }
@@ -243,11 +272,20 @@ __device__ __forceinline__ void dp_stage(const typename Op::T *__restrict__ prev
         A[t] = ga[-t];
       }
     }
-    const int iters = 2 * r0 + nbr + 1;  // (bA+1) + (bB+1) for every folded lane
-    for (int it = 0; it < iters; it += 2) {
+    // (bA+1) + (bB+1) steps for every folded lane; exactly `iters` of them run, the last one as a diagonal tile
+    const int iters = 2 * r0 + nbr + 1;
+    int it = 0;
+    for (; it + 2 < iters; it += 2) {
       tile_step<J, Op>(A, B, acc, st, prev, cur, G, P, lowest);
       tile_step<J, Op>(B, A, acc, st, prev, cur, G, P, lowest);
     }
+    if (iters - it == 2) {
+      tile_step<J, Op>(A, B, acc, st, prev, cur, G, P, lowest);  // leaves the current window in B
+    } else {
+#pragma unroll
+      for (int t = 0; t < J; ++t) B[t] = A[t];
+    }
+    tile_last<J, Op>(B, acc, st, prev, cur, G, lowest);
     if (st.kstep) {  // the last job of this lane has not been flushed by a later step
       T *dst = cur + st.b * J;
 #pragma unroll
