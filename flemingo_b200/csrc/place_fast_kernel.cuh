@@ -447,6 +447,7 @@ __device__ __forceinline__ void refine_round(const FastParams &f, const OrgView 
   }
   const unsigned char *my_bins = p.bins + (size_t)my_seq * p.bins_row_stride;
   bool my_failed = false;
+  bool my_single = true;  // every candidate list of this pair holds exactly one cell
   auto row_s = [&](int i) { return my_rows + (size_t)(i & 1) * f.rowq_stride; };
   // streams row i (<= n-3) of the team's pair from global scratch into its ping-pong buffer; the caller makes sure
   // the buffer's previous content (row i+2) is dead and waits (cp_async_wait_all + __syncwarp) before reading
@@ -485,19 +486,24 @@ __device__ __forceinline__ void refine_round(const FastParams &f, const OrgView 
     const int thr = mx - plan.thr_final;
     int count = 0;
     for (int k0 = 0; k0 < P; k0 += 32 * TEAM) {
-      // predicated, fully unrolled: the 32 loads are independent and go out back to back
-      int x[32];
-#pragma unroll
-      for (int b = 0; b < 32; ++b) {
-        const int k = k0 + TEAM * b + tl;
-        x[b] = (k < P) ? row[k] : kLowest;
-      }
+      // predicated and unrolled in chunks of 8 independent loads
       unsigned m = 0;
+      for (int b0 = 0; b0 < 32 && k0 + TEAM * b0 < P; b0 += 8) {
+        int x[8];
 #pragma unroll
-      for (int b = 0; b < 32; ++b) m |= (x[b] >= thr ? 1u : 0u) << b;
+        for (int b = 0; b < 8; ++b) {
+          const int k = k0 + TEAM * (b0 + b) + tl;
+          x[b] = (k < P) ? row[k] : kLowest;
+        }
+        unsigned mm = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) mm |= (x[b] >= thr ? 1u : 0u) << b;
+        m |= mm << b0;
+      }
       emit(my_active ? m : 0u, k0, n - 1, count);
     }
     if (count > CAP) my_failed = true;
+    my_single = my_single && (count == 1);
     if (tl == 0) cn[team * p.max_rec + n - 1] = min(count, CAP);
   }
   __syncwarp();
@@ -547,8 +553,10 @@ __device__ __forceinline__ void refine_round(const FastParams &f, const OrgView 
             const int k = k0 + TEAM * (b0 + b) + tl;
             x[b] = (k <= j0) ? prev[k] + Gq[j0 - k] : kLowest;
           }
+          unsigned mm = 0;
 #pragma unroll
-          for (int b = 0; b < 8; ++b) m |= (x[b] >= thr[0] ? 1u : 0u) << (b0 + b);
+          for (int b = 0; b < 8; ++b) mm |= (x[b] >= thr[0] ? 1u : 0u) << b;
+          m |= mm << b0;
         }
       } else {
         for (int b = 0; b < 32; ++b) {
@@ -566,6 +574,7 @@ __device__ __forceinline__ void refine_round(const FastParams &f, const OrgView 
       emit(m, k0, i - 1, count);
     }
     if (count > CAP) my_failed = true;
+    my_single = my_single && (count == 1);
     if (tl == 0) cn[team * p.max_rec + i - 1] = min(count, CAP);
     __syncwarp();
   }
@@ -580,12 +589,8 @@ __device__ __forceinline__ void refine_round(const FastParams &f, const OrgView 
   // (3) exact scores of every candidate cell (they do not depend on the chain): lanes = (pair, stage) when every
   //     list holds one cell, otherwise list by list
   {
-    bool one_each = (NT * n <= 32);
-#pragma unroll
-    for (int t = 0; t < NT; ++t) {
-      if (!okp[t]) continue;
-      for (int i = 0; i < n; ++i) one_each = one_each && (cn[t * p.max_rec + i] == 1);
-    }
+    // pairs that are not refined (declined or failed) do not matter for the layout choice
+    const bool one_each = (NT * n <= 32) && __all_sync(0xffffffffu, my_single || !my_active || my_failed);
     if (one_each) {
       const int t = lane / n, i = lane - t * n;
       if (t < NT && pick(okp, t)) {
