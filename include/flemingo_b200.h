@@ -11,6 +11,8 @@
  *     exit(1) on a NaN null-model bin, extensions/multiplacement/src/organism/recognizer.c:258-262);
  *   - all device work of a context is issued on ONE stream (fl_ctx_stream); calls that return host data
  *     synchronise that stream, the others are asynchronous until fl_sync();
+ *   - input buffers may be reused or freed as soon as a call returns: copies from pageable memory are staged
+ *     before the call returns, and an upload whose source is pinned (page-locked) memory synchronises the stream;
  *   - one context per process and device; contexts are not thread-safe (the reference holds the GIL for the
  *     whole call, src/_interface.c:45-185).
  */
