@@ -279,10 +279,14 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # end to end through the public host API (Python organisms + str sequences in, statistics out).
     # e2e: EVERYTHING is re-uploaded every step (population and both DNA sets); e2e_resident: the population is
     # uploaded every step, the DNA sets -- which a GA run never changes between generations -- stay in HBM.
-    e2e_steps = max(1, min(args.steps, 5))
+    # The same W warm-up calls as the device-timed loop (at least 3): the first calls after start-up run 1-2 ms slower
+    # (allocator growth, page faults on fresh host arrays), tools/e2e_iterations.py.
+    e2e_steps = max(1, min(args.steps, 10))
+    e2e_warmup = max(3, args.warmup)
 
     def e2e_loop(reuse):
-        set_population_fitness(orgs, pos, neg, "Welch", 0.2, engine=eng, reuse_sets=reuse)
+        for _ in range(e2e_warmup):
+            set_population_fitness(orgs, pos, neg, "Welch", 0.2, engine=eng, reuse_sets=reuse)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
@@ -329,7 +333,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": bench_config(args, w, n_org_total), "clocks": clocks,
                 "e2e": {"value": placements / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_s * 1e3},
+                        "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "warmup": e2e_warmup},
                 "e2e_resident_sets": {"value": placements / e2e_res_s, "unit": UNIT, "h2d_bytes_per_step": pop_bytes,
                                       "d2h_bytes_per_step": d2h, "ms_per_step": e2e_res_s * 1e3,
                                       "note": "population uploaded every step; the two DNA sets stay resident in HBM"},

@@ -188,8 +188,9 @@ def pack_population(organisms) -> PackedPopulation:
     org_of = np.repeat(np.arange(n_org), n_rec)
     seg_first = rec_begin[:-1].astype(np.int64)
 
-    pssm_parts = [_f64(org.recognizers_flat) for org in organisms]
-    pssm_sizes = np.fromiter((a.size for a in pssm_parts), dtype=np.int64, count=n_org)
+    # parts are concatenated as they are (numpy converts lists / other dtypes on the way); sizes come from len()
+    pssm_parts = [org.recognizers_flat for org in organisms]
+    pssm_sizes = np.fromiter(map(len, pssm_parts), dtype=np.int64, count=n_org)
     size_p = np.where(is_p, 4 * rec_len.astype(np.int64), 0)
     if not np.array_equal(np.bincount(org_of, weights=size_p, minlength=n_org).astype(np.int64), pssm_sizes):
         raise ValueError("recognizers_flat does not match the PSSM lengths of an organism")
@@ -202,8 +203,8 @@ def pack_population(organisms) -> PackedPopulation:
     cls_edges = np.zeros(0, np.int64)
     edges_pool = np.zeros(0, np.float64)
     if any_shape:
-        model_parts = [_f64(org.recognizer_models) for org in organisms]
-        model_sizes = np.fromiter((a.size for a in model_parts), dtype=np.int64, count=n_org)
+        model_parts = [org.recognizer_models for org in organisms]
+        model_sizes = np.fromiter(map(len, model_parts), dtype=np.int64, count=n_org)
         nb_shapes = np.concatenate([np.asarray(org.recognizer_bin_nums, dtype=np.int32) for org in organisms])
         shape_idx = np.nonzero(~is_p)[0]
         if nb_shapes.size != shape_idx.size:
@@ -215,7 +216,7 @@ def pack_population(organisms) -> PackedPopulation:
         pool_parts = [x for pair in zip(pssm_parts, model_parts) for x in pair]
         org_pool = pssm_sizes + model_sizes
         # shape classes: distinct (kind, length, edges) -- grouped by the number of edges so rows can be compared
-        all_edges = np.concatenate([_f64(org.recognizer_bin_edges) for org in organisms])
+        all_edges = np.concatenate([org.recognizer_bin_edges for org in organisms]).astype(np.float64, copy=False)
         if all_edges.size != int(nb_shapes.sum()):
             raise ValueError("recognizer_bin_edges does not match recognizer_bin_nums")
         e_start = np.cumsum(nb_shapes, dtype=np.int64) - nb_shapes
@@ -249,31 +250,33 @@ def pack_population(organisms) -> PackedPopulation:
         org_pool = pssm_sizes
     pool_begin = np.zeros(n_org + 1, dtype=np.int64)
     np.cumsum(org_pool, out=pool_begin[1:])
-    rec_pool = np.concatenate(pool_parts) if n_org else np.zeros(0)
+    rec_pool = np.concatenate(pool_parts).astype(np.float64, copy=False) if n_org else np.zeros(0)
     # recognizer data offsets: PSSMs in order inside the organism's PSSM segment, shape models in order inside its model segment
     off_p = _segment_exclusive_cumsum(size_p, seg_first, org_of)
     off_m = _segment_exclusive_cumsum(size_m, seg_first, org_of)
     rec_data = pool_begin[:-1][org_of] + np.where(is_p, off_p, pssm_sizes[org_of] + off_m)
 
     sum_len = np.bincount(org_of, weights=rec_len, minlength=n_org).astype(np.int32) if n_total else np.zeros(n_org, np.int32)
-    con_parts = [_f64(org.connectors_scores_flat) for org in organisms]
-    con_sizes = np.fromiter((a.size for a in con_parts), dtype=np.int64, count=n_org)
+    con_parts = [org.connectors_scores_flat for org in organisms]
+    con_sizes = np.fromiter(map(len, con_parts), dtype=np.int64, count=n_org)
     multi = n_rec > 1
     if bool(np.any(multi & (con_sizes == 2 * (n_rec - 1)))):
         raise NotImplementedError(
             "organism.PRECOMPUTE=false (connectors without pdf/cdf tables) uses the reference's legacy "
             "float maths (connector.c:70-72, _aux.c:47-139); the GPU path requires precomputed tables")
-    con_M = np.zeros(n_org, dtype=np.int32)
-    pcs = np.zeros(n_org, dtype=np.float64)
-    for o in np.nonzero(multi)[0]:
-        first = organisms[o].connectors[0]
-        con_M[o] = first.max_seq_length
-        pcs[o] = first.pseudo_count
+    firsts = [org.connectors[0] if m else None for org, m in zip(organisms, multi.tolist())]
+    con_M = np.fromiter((f.max_seq_length if f is not None else 0 for f in firsts), dtype=np.int32, count=n_org)
+    pcs = np.fromiter((f.pseudo_count if f is not None else 0.0 for f in firsts), dtype=np.float64, count=n_org)
     if bool(np.any(multi & (con_sizes != (n_rec - 1) * (2 * con_M.astype(np.int64) + 2)))):
         raise ValueError("connectors_scores_flat does not match (n-1) * (2*max_seq_length + 2)")
     con_sizes = np.where(multi, con_sizes, 0)
     con_base = np.cumsum(con_sizes) - con_sizes
-    con_pool = np.concatenate([c for c, m in zip(con_parts, multi) if m]) if bool(multi.any()) else np.zeros(0)
+    if bool(multi.all()):
+        con_pool = np.concatenate(con_parts).astype(np.float64, copy=False)
+    elif bool(multi.any()):
+        con_pool = np.concatenate([c for c, m in zip(con_parts, multi) if m]).astype(np.float64, copy=False)
+    else:
+        con_pool = np.zeros(0)
     return PackedPopulation(
         n_org=n_org, rec_begin=rec_begin, rec_type=np.ascontiguousarray(rec_type), rec_len=np.ascontiguousarray(rec_len),
         rec_nb=rec_nb, rec_data=np.ascontiguousarray(rec_data, dtype=np.int64), pool_begin=pool_begin,
