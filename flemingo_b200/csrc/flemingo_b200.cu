@@ -667,7 +667,9 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
       fast_rowq[j] = (Pmax + kFastConfigs[j].J + 3) & ~3;
       fast_slot[j] = ((2 * fast_rowq[j] + 31) & ~31) + (team & 31);
       int best_occ = 0;
-      static const int kWarpChoices[] = {16, 14, 12, 10, 8, 7, 6, 4, 2, 1};
+      // multiples of four only: the DP stages are bound by the ALU pipe of each of the SM's four schedulers, so a
+      // scheduler that holds one warp more than the others sets the pace (13 warps: 194 ms on config 3, 12 warps: 169 ms)
+      static const int kWarpChoices[] = {16, 12, 8, 4, 2, 1};
       const char *force_w = getenv("FLEMINGO_FAST_WARPS");
       for (int nw : kWarpChoices) {
         if (force_w && atoi(force_w) != nw) continue;
