@@ -658,6 +658,7 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
     // fast-path geometry: warps per CTA chosen for the most resident warps per SM; if even one warp does not fit,
     // those organisms go to the exact kernel
     int fast_warps[kNumFastConfigs], fast_rowq[kNumFastConfigs], fast_slot[kNumFastConfigs], fast_ctas_per_sm[kNumFastConfigs];
+    bool fast_single[kNumFastConfigs] = {false};
     size_t fast_smem[kNumFastConfigs];
     for (int j = 0; j < kNumFastConfigs; ++j) {
       fast_warps[j] = 0;
@@ -665,27 +666,35 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
       if (fast_bucket[j].empty()) continue;
       const int team = kFastConfigs[j].team, nt = 32 / team;
       fast_rowq[j] = (Pmax + kFastConfigs[j].J + 3) & ~3;
-      fast_slot[j] = ((2 * fast_rowq[j] + 31) & ~31) + (team & 31);
       int best_occ = 0;
       // multiples of four only: the DP stages are bound by the ALU pipe of each of the SM's four schedulers, so a
       // scheduler that holds one warp more than the others sets the pace (13 warps: 194 ms on config 3, 12 warps: 169 ms)
       static const int kWarpChoices[] = {16, 12, 8, 4, 2, 1};
       const char *force_w = getenv("FLEMINGO_FAST_WARPS");
-      for (int nw : kWarpChoices) {
-        if (force_w && atoi(force_w) != nw) continue;
-        const size_t d = (size_t)pp.pool_stride + (size_t)(P.max_rec - 1) * pp.g_stride + 2ull * nw * P.max_rec * kCandCap;
-        const size_t i = (size_t)(P.max_rec - 1) * fp.gq_stride + fp.kmer_cap + (size_t)nw * nt * fast_slot[j] +
-                         2ull * nw * P.max_rec * kCandCap + (size_t)nw * nt * P.max_rec;
-        const size_t bytes = d * 8 + i * 4 + sizeof(RecDesc) * P.max_rec + sizeof(FastPlan) + 48 + (size_t)nw * nt * fp.k8_stride;
-        if (bytes > (size_t)kMaxSmem) continue;
-        const int ctas = (int)std::min<size_t>(233472 / (bytes + 1024), 32);
-        const int reg_warps = ctx->fast_reg_warps[j];  // 16-19 for the 101-124 registers ptxas settles at
-        const int occ = std::min(ctas * nw, reg_warps);
-        if (occ > best_occ) {
-          best_occ = occ;
-          fast_warps[j] = nw;
-          fast_smem[j] = bytes;
-          fast_ctas_per_sm[j] = std::max(1, std::min(ctas, reg_warps / nw));
+      // two quantised rows per pair (ping-pong; the refinement prefetches older rows behind its scans) unless ONE row
+      // (in-place stages, older rows fetched on demand) lets more warps live on the SM
+      const char *force_rows = getenv("FLEMINGO_FAST_ROWS");
+      for (int rows = 2; rows >= 1; --rows) {
+        if (force_rows && atoi(force_rows) != rows) continue;
+        const int slot = ((rows * fast_rowq[j] + 31) & ~31) + (team & 31);
+        for (int nw : kWarpChoices) {
+          if (force_w && atoi(force_w) != nw) continue;
+          const size_t d = (size_t)pp.pool_stride + (size_t)(P.max_rec - 1) * pp.g_stride + 2ull * nw * P.max_rec * kCandCap;
+          const size_t i = (size_t)(P.max_rec - 1) * fp.gq_stride + fp.kmer_cap + (size_t)nw * nt * slot +
+                           2ull * nw * P.max_rec * kCandCap + (size_t)nw * nt * P.max_rec;
+          const size_t bytes = d * 8 + i * 4 + sizeof(RecDesc) * P.max_rec + sizeof(FastPlan) + 48 + (size_t)nw * nt * fp.k8_stride;
+          if (bytes > (size_t)kMaxSmem) continue;
+          const int ctas = (int)std::min<size_t>(233472 / (bytes + 1024), 32);
+          const int reg_warps = ctx->fast_reg_warps[j];  // 16-19 for the 101-124 registers ptxas settles at
+          const int occ = nw * std::min(ctas, reg_warps / nw);  // whole CTAs only
+          if (occ > best_occ) {
+            best_occ = occ;
+            fast_warps[j] = nw;
+            fast_smem[j] = bytes;
+            fast_slot[j] = slot;
+            fast_single[j] = rows == 1;
+            fast_ctas_per_sm[j] = std::max(1, std::min(ctas, reg_warps / nw));
+          }
         }
       }
       if (!fast_warps[j]) {
@@ -740,6 +749,7 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
         const int team = kFastConfigs[j].team, nt = 32 / team, nw = fast_warps[j];
         fp.rowq_stride = fast_rowq[j];
         fp.slotq_stride = fast_slot[j];
+        fp.single_row = fast_single[j] ? 1 : 0;
         fp.scratch_slot_stride = (long long)P.max_rec * fast_rowq[j];
         const int per_round = nw * nt;
         const long long pairs = (long long)n_b * cl.count;
@@ -760,8 +770,8 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
         fp.work_counter = ctx->work_counters.as<int>() + (ctx->launches % 1024);
         CK(cudaMemsetAsync(fp.work_counter, 0, sizeof(int), ctx->stream));
         if (getenv("FLEMINGO_DEBUG_LAUNCH"))
-          fprintf(stderr, "fast launch: cfg J=%d team=%d warps=%d ctas/sm=%d grid=%lld items=%lld spc=%d smem=%zu\n", kFastConfigs[j].J, team, nw,
-                  fast_ctas_per_sm[j], grid, items, spc, fast_smem[j]);
+          fprintf(stderr, "fast launch: cfg J=%d team=%d warps=%d ctas/sm=%d grid=%lld items=%lld spc=%d smem=%zu rows=%d\n", kFastConfigs[j].J, team, nw,
+                  fast_ctas_per_sm[j], grid, items, spc, fast_smem[j], fast_single[j] ? 1 : 2);
         kFastConfigs[j].fn<<<(unsigned)grid, nw * 32, fast_smem[j], ctx->stream>>>(fp);
         CK(cudaGetLastError());
         ctx->launches++;

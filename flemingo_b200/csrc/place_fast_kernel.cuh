@@ -33,7 +33,10 @@ struct FastParams {
   int fb_cap;
   int gq_stride;     // ints per quantised connector table (kGPad + Pmax + kGPad)
   int rowq_stride;   // ints per quantised row
-  int slotq_stride;  // ints per pair slot (2 ping-pong rows), == TEAM (mod 32) so that teams hit disjoint banks
+  int slotq_stride;  // ints per pair slot (1 or 2 rows), == TEAM (mod 32) so that teams hit disjoint banks
+  int single_row;    // 1: ONE quantised row per pair in shared memory -- the DP stage runs in place (dp_stage) and every
+                     // older row is streamed back from global scratch when the refinement needs it; chosen by the host
+                     // when halving the row storage lets more warps (a higher multiple of four) live on an SM
   int k8_stride;     // bytes per 4-mer code array (S + kK8Pad rounded up to 16)
   int kmer_cap;      // ints available for the 4-mer tables of one organism
   int want_trace;
@@ -448,7 +451,8 @@ __device__ __forceinline__ void refine_round(const FastParams &f, const OrgView 
   const unsigned char *my_bins = p.bins + (size_t)my_seq * p.bins_row_stride;
   bool my_failed = false;
   bool my_single = true;  // every candidate list of this pair holds exactly one cell
-  auto row_s = [&](int i) { return my_rows + (size_t)(i & 1) * f.rowq_stride; };
+  const bool single = f.single_row != 0;
+  auto row_s = [&](int i) { return my_rows + (single ? (size_t)0 : (size_t)(i & 1) * f.rowq_stride); };
   // streams row i (<= n-3) of the team's pair from global scratch into its ping-pong buffer; the caller makes sure
   // the buffer's previous content (row i+2) is dead and waits (cp_async_wait_all + __syncwarp) before reading
   const int row_chunks = (P + 3) >> 2;
@@ -514,12 +518,12 @@ __device__ __forceinline__ void refine_round(const FastParams &f, const OrgView 
   for (int i = n - 1; i >= 1; --i) {
     const int *Gq = sm.Gq + (size_t)(i - 1) * f.gq_stride + kGPad;
     const RecDesc rdi = sm.rec[i];
-    if (i - 1 <= n - 3) {  // row i-1 was requested during the previous stage
+    if (!single && i - 1 <= n - 3) {  // row i-1 was requested during the previous stage
       cp_async_wait_all();
       __syncwarp();
     }
     const int *prev = row_s(i - 1);
-    const int *cur = row_s(i);
+    const int *cur = row_s(i);  // one-row mode: the same buffer; row i-1 replaces row i once the thresholds are known
     const int cnt = (my_active && !my_failed) ? cn[team * p.max_rec + i] : 0;
     int cmax = cnt, jj[CAP], thr[CAP], jmax = -1;
 #pragma unroll
@@ -536,7 +540,12 @@ __device__ __forceinline__ void refine_round(const FastParams &f, const OrgView 
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) jmax = max(jmax, __shfl_xor_sync(0xffffffffu, jmax, o));
-    if (i >= 2) {  // row i is dead from here on: its buffer receives row i-2 while row i-1 is scanned
+    if (single) {  // row i is dead from here on: row i-1 takes its place (the scan has to wait for it)
+      __syncwarp();
+      prefetch_row(i - 1);
+      cp_async_wait_all();
+      __syncwarp();
+    } else if (i >= 2) {  // row i is dead from here on: its buffer receives row i-2 while row i-1 is scanned
       __syncwarp();
       prefetch_row(i - 2);
     }
@@ -842,13 +851,15 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
       PHASE_MARK(2);
       const unsigned char *bins_seq = p.bins + (size_t)seq * p.bins_row_stride;
       const size_t cls_stride = (size_t)p.n_seq_total * p.bins_row_stride;
-      add_scores_q<J, TEAM, true>(plan, 0, sm.rec[0], sm.kmer, k8, bins_seq, cls_stride, rowsq, (0 <= n - 3) ? rowsg : nullptr, P, tl,
+      // rows the refinement will have to fetch from global scratch: all but the last two (two-row mode) or the last one
+      const int last_mirrored = n - 2 - (f.single_row ? 0 : 1);
+      add_scores_q<J, TEAM, true>(plan, 0, sm.rec[0], sm.kmer, k8, bins_seq, cls_stride, rowsq, (0 <= last_mirrored) ? rowsg : nullptr, P, tl,
                                   nan_hit, row_max);
       __syncwarp();
       PHASE_MARK(3);
       for (int i = 1; i < n; ++i) {
-        const int *prev = rowsq + (size_t)((i - 1) & 1) * f.rowq_stride;
-        int *cur = rowsq + (size_t)(i & 1) * f.rowq_stride;
+        const int *prev = f.single_row ? rowsq : rowsq + (size_t)((i - 1) & 1) * f.rowq_stride;
+        int *cur = f.single_row ? rowsq : rowsq + (size_t)(i & 1) * f.rowq_stride;
         const int *Gq = sm.Gq + (size_t)(i - 1) * f.gq_stride + kGPad;
 #ifdef FL_SKIP_DP       // profiling only: marginal cost of the DP stages (results are wrong)
         for (int j = tl; j < P; j += TEAM) cur[j] = prev[j] + Gq[j & 15];
@@ -858,7 +869,7 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
         __syncwarp();
         PHASE_MARK(4);
         add_scores_q<J, TEAM, false>(plan, i, sm.rec[i], sm.kmer, k8, bins_seq, cls_stride, cur,
-                                     (i <= n - 3) ? rowsg + (size_t)i * f.rowq_stride : nullptr, P, tl, nan_hit, row_max);
+                                     (i <= last_mirrored) ? rowsg + (size_t)i * f.rowq_stride : nullptr, P, tl, nan_hit, row_max);
         __syncwarp();
         PHASE_MARK(3);
       }
@@ -880,7 +891,7 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
       }
       PHASE_MARK(6);
 #ifdef FL_SKIP_REFINE   // profiling only: marginal cost of the refinement (results are wrong)
-      if (lane < NT && r_live[lane % NT]) p.E[(size_t)v.o * p.n_seq_total + seq] = (double)rowsq[(size_t)((n - 1) & 1) * f.rowq_stride + P - 1];
+      if (lane < NT && r_live[lane % NT]) p.E[(size_t)v.o * p.n_seq_total + seq] = (double)rowsq[(f.single_row ? (size_t)0 : (size_t)((n - 1) & 1) * f.rowq_stride) + P - 1];
 #pragma unroll
       for (int t = 0; t < NT; ++t) r_failed[t] = false;
 #else

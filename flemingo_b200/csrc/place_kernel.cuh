@@ -165,7 +165,7 @@ struct TileState {
 // rows, then start the folded partner block (or go idle) and load the first window of the new job into `A`.
 template <int J, class Op>
 __device__ __forceinline__ void tile_switch(typename Op::T (&A)[J], typename Op::T (&acc)[J], TileState &st,
-                                            typename Op::T *__restrict__ cur, const typename Op::T *__restrict__ G,
+                                            typename Op::T *cur, const typename Op::T *__restrict__ G,
                                             typename Op::T lowest) {
   typedef typename Op::T T;
   if (st.kb == st.kend) {
@@ -194,8 +194,8 @@ __device__ __forceinline__ void tile_switch(typename Op::T (&A)[J], typename Op:
 
 template <int J, class Op>
 __device__ __forceinline__ void tile_step(typename Op::T (&A)[J], typename Op::T (&B)[J], typename Op::T (&acc)[J],
-                                          TileState &st, const typename Op::T *__restrict__ prev,
-                                          typename Op::T *__restrict__ cur, const typename Op::T *__restrict__ G, int P,
+                                          TileState &st, const typename Op::T *prev,
+                                          typename Op::T *cur, const typename Op::T *__restrict__ G, int P,
                                           typename Op::T lowest) {
   typedef typename Op::T T;
   tile_switch<J, Op>(A, acc, st, cur, G, lowest);
@@ -223,7 +223,7 @@ __device__ __forceinline__ void tile_step(typename Op::T (&A)[J], typename Op::T
 // only the cells k <= j exist -- J(J+1)/2 of the J*J -- and only the `A` window is needed.
 template <int J, class Op>
 __device__ __forceinline__ void tile_last(typename Op::T (&A)[J], typename Op::T (&acc)[J], TileState &st,
-                                          const typename Op::T *__restrict__ prev, typename Op::T *__restrict__ cur,
+                                          const typename Op::T *prev, typename Op::T *cur,
                                           const typename Op::T *__restrict__ G, typename Op::T lowest) {
   typedef typename Op::T T;
   tile_switch<J, Op>(A, acc, st, cur, G, lowest);
@@ -240,22 +240,29 @@ __device__ __forceinline__ void tile_last(typename Op::T (&A)[J], typename Op::T
 }
 
 // `tl` = lane index inside the team (0..TEAM-1).  Rounds of 2*TEAM row blocks; inside a round lane tl owns block
-// tl and the mirrored block, so every lane of the team runs the same number of tiles.
+// r0+tl and the mirrored block r0+nbr-1-tl, so every lane of the team runs the same number of tiles.
+//
+// `cur` may be the SAME buffer as `prev` (in-place stage, one row per pair in shared memory).  That is safe because
+// of the order of the work: rounds run from the highest blocks down, and inside a round a lane does its UPPER block
+// first.  A job on block b starts at k block 0 and is flushed after b+1 steps; every other job of the round that
+// still needs k block b started at the same step 0 and read it at its step b, i.e. before.  The LOWER blocks are all
+// flushed together after the last step, and a lower block only ever reads k blocks below the upper half.  Lower
+// rounds read lower k blocks than anything flushed so far.  (The lanes of a team run these steps in lockstep.)
 template <int J, int TEAM, class Op>
-__device__ __forceinline__ void dp_stage(const typename Op::T *__restrict__ prev, typename Op::T *__restrict__ cur,
+__device__ __forceinline__ void dp_stage(const typename Op::T *prev, typename Op::T *cur,
                                          const typename Op::T *__restrict__ G, int P, int tl, typename Op::T lowest) {
   typedef typename Op::T T;
   const int NB = (P + J - 1) / J;
-  for (int r0 = 0; r0 < NB; r0 += 2 * TEAM) {
+  for (int r0 = ((NB - 1) / (2 * TEAM)) * (2 * TEAM); r0 >= 0; r0 -= 2 * TEAM) {
     const int nbr = min(2 * TEAM, NB - r0);
     const int half = (nbr + 1) >> 1;
     const int bA = r0 + tl, bB = r0 + nbr - 1 - tl;
     TileState st;
     if (tl < half) {
-      st.b = bA;
-      st.kend = bA + 1;
+      st.b = bB;  // upper block first (equal to bA for the middle lane of an odd round: a single job)
+      st.kend = bB + 1;
       st.kstep = 1;
-      st.next_b = (bB > bA) ? bB : -1;
+      st.next_b = (bB > bA) ? bA : -1;
     } else {
       st.b = 0;
       st.kend = -1;
@@ -272,7 +279,8 @@ __device__ __forceinline__ void dp_stage(const typename Op::T *__restrict__ prev
         A[t] = ga[-t];
       }
     }
-    // (bA+1) + (bB+1) steps for every folded lane; exactly `iters` of them run, the last one as a diagonal tile
+    // (bB+1) + (bA+1) steps for every folded lane; exactly `iters` of them run, the last one -- the diagonal tile of
+    // the lower block for every lane -- in its triangular form
     const int iters = 2 * r0 + nbr + 1;
     int it = 0;
     for (; it + 2 < iters; it += 2) {

@@ -39,15 +39,21 @@ def golden_cases(golden, golden_null_models):
     return [(case, build_case_organism(case)) for case in golden["cases"]]
 
 
-@pytest.fixture(scope="session", params=["filter+refine", "exact-only"])
+@pytest.fixture(scope="session", params=["filter+refine", "filter+refine, one row", "exact-only"])
 def engine(request):
-    """The process-wide engine, once with the integer filter pass enabled and once with every pair forced
-    through the exact fp64 kernel -- both must reproduce the reference bit for bit."""
+    """The process-wide engine in its three kernel modes -- integer filter pass with two quantised rows per pair in
+    shared memory (the usual choice), the same with ONE row (in-place DP stages; chosen automatically only when it
+    lets more warps live on an SM, forced here), and every pair through the exact fp64 kernel.  All of them must
+    reproduce the reference bit for bit."""
+    import os
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from flemingo_b200.engine import get_engine
     eng = get_engine()
     eng.exact_only = request.param == "exact-only"
+    if request.param.endswith("one row"):
+        os.environ["FLEMINGO_FAST_ROWS"] = "1"      # read by fl_place_batch at every call
     yield eng
+    os.environ.pop("FLEMINGO_FAST_ROWS", None)
     eng.exact_only = False

@@ -24,6 +24,55 @@ template <int J, int TEAM> int run_i32(int P, unsigned seed) {
   for (int j = 0; j < P; j++) if (cur[j] != ref[j]) bad++;
   return bad;
 }
+
+// In-place stage (cur == prev), with the TEAM lanes advanced in LOCKSTEP the way a warp executes them: within one
+// step every lane's job switch (flush) comes before every lane's loads.  Mirrors the control flow of dp_stage.
+template <int J, int TEAM> int run_i32_inplace(int P, unsigned seed) {
+  srand(seed);
+  const int SENT = -50000000;
+  int NBJ = ((P + J - 1) / J) * J;
+  std::vector<int> row(NBJ + 32, 0), G(P + 2 * kGPad, SENT), ref(P);
+  for (int i = 0; i < P; i++) { row[i] = -(rand() % 1000000); G[kGPad + i] = -(rand() % 1000000); }
+  for (int j = 0; j < P; j++) { int b = SENT; for (int k = 0; k <= j; k++) b = std::max(b, row[k] + G[kGPad + j - k]); ref[j] = b; }
+  const int *Gp = G.data() + kGPad;
+  int *buf = row.data();
+  const int NB = (P + J - 1) / J;
+  for (int r0 = ((NB - 1) / (2 * TEAM)) * (2 * TEAM); r0 >= 0; r0 -= 2 * TEAM) {
+    const int nbr = std::min(2 * TEAM, NB - r0), half = (nbr + 1) >> 1;
+    TileState st[TEAM];
+    int acc[TEAM][J], A[TEAM][J], B[TEAM][J];
+    for (int tl = 0; tl < TEAM; tl++) {
+      const int bA = r0 + tl, bB = r0 + nbr - 1 - tl;
+      if (tl < half) { st[tl].b = bB; st[tl].kend = bB + 1; st[tl].kstep = 1; st[tl].next_b = (bB > bA) ? bA : -1; }
+      else { st[tl].b = 0; st[tl].kend = -1; st[tl].kstep = 0; st[tl].next_b = -1; }
+      st[tl].kb = 0;
+      const int *ga = Gp + st[tl].b * J + (J - 1);
+      for (int t = 0; t < J; t++) { acc[tl][t] = SENT; A[tl][t] = ga[-t]; }
+    }
+    const int iters = 2 * r0 + nbr + 1;
+    bool a_role = true;  // which array currently plays the A role
+    for (int it = 0; it < iters; it++) {
+      const bool last = (it == iters - 1);
+      for (int tl = 0; tl < TEAM; tl++) {  // phase 1: job switches of every lane
+        if (a_role) tile_switch<J, OpI32>(A[tl], acc[tl], st[tl], buf, Gp, SENT);
+        else tile_switch<J, OpI32>(B[tl], acc[tl], st[tl], buf, Gp, SENT);
+      }
+      for (int tl = 0; tl < TEAM; tl++) {  // phase 2: loads and cells (the switch inside is a no-op now)
+        if (last) {
+          if (a_role) tile_last<J, OpI32>(A[tl], acc[tl], st[tl], buf, buf, Gp, SENT);
+          else tile_last<J, OpI32>(B[tl], acc[tl], st[tl], buf, buf, Gp, SENT);
+        } else if (a_role) tile_step<J, OpI32>(A[tl], B[tl], acc[tl], st[tl], buf, buf, Gp, P, SENT);
+        else tile_step<J, OpI32>(B[tl], A[tl], acc[tl], st[tl], buf, buf, Gp, P, SENT);
+      }
+      a_role = !a_role;
+    }
+    for (int tl = 0; tl < TEAM; tl++)
+      if (st[tl].kstep) for (int t = 0; t < J; t++) buf[st[tl].b * J + t] = acc[tl][t];
+  }
+  int bad = 0;
+  for (int j = 0; j < P; j++) if (buf[j] != ref[j]) bad++;
+  return bad;
+}
 template <int J> int run(int P, unsigned seed) {
   srand(seed);
   int NBJ = ((P + J - 1) / J) * J;
@@ -42,6 +91,9 @@ int main() {
     int b = run<1>(P, P) + run<3>(P, P + 1) + run<5>(P, P + 2) + run<7>(P, P + 3) + run<9>(P, P + 4);
     b += run_i32<17, 8>(P, P + 5) + run_i32<19, 8>(P, P + 6) + run_i32<9, 16>(P, P + 7) + run_i32<13, 32>(P, P + 8) +
          run_i32<3, 8>(P, P + 9) + run_i32<21, 8>(P, P + 10) + run_i32<11, 16>(P, P + 11);
+    b += run_i32_inplace<17, 8>(P, P + 12) + run_i32_inplace<19, 8>(P, P + 13) + run_i32_inplace<9, 16>(P, P + 14) +
+         run_i32_inplace<13, 32>(P, P + 15) + run_i32_inplace<3, 8>(P, P + 16) + run_i32_inplace<21, 16>(P, P + 17) +
+         run_i32_inplace<5, 8>(P, P + 18);
     if (b) printf("P=%d bad=%d\n", P, b);
     total += b;
   }
