@@ -361,12 +361,17 @@ __device__ void build_fast_plan(const FastParams &f, const OrgView &v, const Fas
 }
 
 // ---- exact refinement of the warp's NT pairs on their candidate sets ---------------------------------------------
-// The NT pairs a warp has just pushed through the integer pass are refined TOGETHER: every step is written over the
-// pair index t so that the NT dependency chains (row maxima, warp votes, score chains) interleave, and the per-pair
-// scalar work (exact recurrence, outputs) runs on NT lanes at once instead of NT times on one lane.
-// Candidate lists hold kCandCap / NT cells per stage and pair; a pair that needs more is handed to the exact kernel.
-// Quantised row i of a pair lives in the shared ping-pong buffer (i & 1): rows n-1 and n-2 are still there after the
-// forward pass, older rows are streamed back from global scratch (cp.async) one stage ahead of the scan that needs them.
+// The NT pairs a warp has just pushed through the integer pass are refined TOGETHER.  Steps (1) and (2) -- the
+// candidate cells of the last row and, top down, of every earlier stage -- run team-parallel: the TEAM lanes of a
+// pair scan that pair's rows, all NT pairs in the same instructions; a lane collects a bitmask of the cells that pass
+// the threshold and a min-reduction loop emits them in ascending order.  Steps (3)-(5) -- exact scores of the
+// candidates, exact forward recurrence, first maximum and traceback -- run with one lane per (pair, stage) or
+// (pair, candidate).  Candidate lists hold kCandCap / NT cells per stage and pair; a pair that needs more is handed
+// to the exact kernel.
+// Quantised rows.  Two-row mode: row i lives in the ping-pong buffer (i & 1); rows n-1 and n-2 are still in shared
+// memory after the forward pass, older rows are streamed back from global scratch (cp.async) one stage ahead of the
+// scan that needs them.  One-row mode (FastParams::single_row): only row n-1 is there, every older row is fetched when
+// its scan starts.
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
