@@ -198,6 +198,8 @@ __device__ __forceinline__ void tile_step(typename Op::T (&A)[J], typename Op::T
                                           typename Op::T *cur, const typename Op::T *__restrict__ G, int P,
                                           typename Op::T lowest) {
   typedef typename Op::T T;
+  // in-place stages: the loads every lane did in the previous step are ordered before the flush a lane may do now
+  __syncwarp();
   tile_switch<J, Op>(A, acc, st, cur, G, lowest);
   // A[i] = G[c - i], B[i] = G[c - J - i] with c = (b - kb)*J + J-1: row t at step u needs G[(b-kb)*J + t - u]
   const T *gb = G + (st.b - st.kb) * J - 1;
@@ -226,6 +228,7 @@ __device__ __forceinline__ void tile_last(typename Op::T (&A)[J], typename Op::T
                                           const typename Op::T *prev, typename Op::T *cur,
                                           const typename Op::T *__restrict__ G, typename Op::T lowest) {
   typedef typename Op::T T;
+  __syncwarp();
   tile_switch<J, Op>(A, acc, st, cur, G, lowest);
   const T *pk = prev + st.kb * J;
   T pv[J];
@@ -294,6 +297,7 @@ __device__ __forceinline__ void dp_stage(const typename Op::T *prev, typename Op
       for (int t = 0; t < J; ++t) B[t] = A[t];
     }
     tile_last<J, Op>(B, acc, st, prev, cur, G, lowest);
+    __syncwarp();
     if (st.kstep) {  // the last job of this lane has not been flushed by a later step
       T *dst = cur + st.b * J;
 #pragma unroll

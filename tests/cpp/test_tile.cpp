@@ -7,6 +7,7 @@
 #define __device__
 #define __forceinline__ inline
 #define __restrict__
+static inline void __syncwarp() {}
 using std::min;
 static inline double neg_inf() { return -std::numeric_limits<double>::infinity(); }
 constexpr int kGPad = 32;
