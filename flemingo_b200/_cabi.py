@@ -21,7 +21,9 @@ FIT_METHODS = {"Welch": 0, "Yuen": 1, "Trim-left-M": 2, "Trim-left-M-SD": 3}
 EXPORTED = [
     "fl_last_error", "fl_abi_version", "fl_ctx_create", "fl_ctx_destroy", "fl_ctx_stream", "fl_sync",
     "fl_upload_sequences", "fl_sequence_classes", "fl_upload_population", "fl_update_connectors", "fl_place_batch", "fl_fitness",
-    "fl_calculate", "fl_launch_count", "fl_path_stats",
+    "fl_fitness_dev",
+    "fl_calculate", "fl_launch_count", "fl_path_stats", "fl_measure_dpx_rate",
+    "fl_build_connector_tables", "fl_round_decimals", "fl_build_shape_masses",
 ]
 
 
@@ -71,7 +73,12 @@ def load_library() -> C.CDLL:
     lib.fl_update_connectors.argtypes = [vp, vp, ll]
     lib.fl_place_batch.argtypes = [vp, ip, vp, ip, vp, vp, vp, vp]
     lib.fl_fitness.argtypes = [vp, ip, ip, ip, dp, vp]
+    lib.fl_fitness_dev.argtypes = [vp, ip, ip, ip, dp, ip, C.POINTER(vp)]
     lib.fl_calculate.argtypes = [vp, vp, ip, vp, ip, vp, vp, vp, ll, vp, vp, vp, ip, vp, vp, vp]
+    lib.fl_measure_dpx_rate.argtypes = [vp, C.POINTER(dp), C.POINTER(dp), C.POINTER(ip), C.POINTER(ip)]
+    lib.fl_build_connector_tables.argtypes = [vp, vp, ip, ip, dp, vp, vp, ip]
+    lib.fl_round_decimals.argtypes = [vp, ll, ip]
+    lib.fl_build_shape_masses.argtypes = [vp, vp, vp, vp, vp, ip, dp, vp, vp]
     lib.fl_path_stats.argtypes = [vp, C.POINTER(ll), C.POINTER(ll)]
     lib.fl_launch_count.restype = ll
     lib.fl_launch_count.argtypes = [vp]

@@ -65,6 +65,12 @@ static const place_kernel_fn kPlaceKernels[kNumTileSizes][2] = {
     {place_tiled_kernel<5, false>, place_tiled_kernel<5, true>}, {place_tiled_kernel<7, false>, place_tiled_kernel<7, true>},
     {place_tiled_kernel<9, false>, place_tiled_kernel<9, true>}};
 
+typedef void (*list_kernel_fn)(const PlaceParams, const ListBuckets, const int *, const int *, unsigned long long *);
+static const list_kernel_fn kListKernels[kNumTileSizes][2] = {
+    {place_list_kernel<1, false>, place_list_kernel<1, true>}, {place_list_kernel<3, false>, place_list_kernel<3, true>},
+    {place_list_kernel<5, false>, place_list_kernel<5, true>}, {place_list_kernel<7, false>, place_list_kernel<7, true>},
+    {place_list_kernel<9, false>, place_list_kernel<9, true>}};
+
 // Tile size for P offsets: the smallest J whose single folded round (64 blocks) covers P, so that most lanes are busy.
 static int pick_tile(int P) {
   for (int j = 0; j < kNumTileSizes; ++j)
@@ -118,13 +124,17 @@ static int pick_fast(int P) {
 struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
+  // `cap` is what callers may ask for; every allocation carries kSlack more bytes that are never handed out, so
+  // the word-sized over-reads of the kernels (up to 16 bytes past the last element) stay inside the allocation
+  // even when a later request fills the capacity exactly.
+  static constexpr size_t kSlack = 256;
   int ensure(size_t bytes) {
-    if (bytes <= cap) return FL_OK;
+    if (bytes <= cap && p) return FL_OK;
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
-    size_t want = bytes + bytes / 4 + 256;
-    CK(cudaMalloc(&p, want));
+    const size_t want = bytes + bytes / 4;
+    CK(cudaMalloc(&p, want + kSlack));
     cap = want;
     return FL_OK;
   }
@@ -169,7 +179,7 @@ struct Population {
 struct fl_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  DevBuf tables, err_flag, con_begin, org_list, gaps, rsc, csc, fit_out, fit_scratch, fb_count, fb_pairs, fast_scratch, fb_total, work_counters;
+  DevBuf tables, err_flag, con_begin, org_list, gaps, rsc, csc, fit_out, fit_scratch, fb_item_count, fb_item_seqs, fast_scratch, fb_total, work_counters;
   int fast_reg_warps[64] = {0};
   long long fast_pairs = 0, fallback_pairs = 0;  // statistics of the last fl_place_batch
   Population pop, scratch_pop;
@@ -196,7 +206,6 @@ extern "C" int fl_ctx_create(int device, const double *tables, long long n_table
   }
   int rc = ctx->tables.ensure(sizeof(double) * FL_N_TABLE_DOUBLES);
   if (rc == FL_OK) rc = ctx->err_flag.ensure(sizeof(int));
-  if (rc == FL_OK) rc = ctx->fb_count.ensure(sizeof(int));
   if (rc == FL_OK) rc = ctx->fb_total.ensure(sizeof(unsigned long long));
   if (rc == FL_OK) rc = ctx->work_counters.ensure(1024 * sizeof(int));
   if (rc == FL_OK && cudaMemsetAsync(ctx->fb_total.p, 0, sizeof(unsigned long long), ctx->stream) != cudaSuccess) rc = fail(FL_E_CUDA, "memset failed");
@@ -219,8 +228,10 @@ extern "C" int fl_ctx_create(int device, const double *tables, long long n_table
     const int regs = std::max(8, (fa.numRegs + 7) & ~7);
     ctx->fast_reg_warps[j] = std::max(1, 65536 / (regs * 32));
   }
-  CK(cudaFuncSetAttribute(place_list_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-  CK(cudaFuncSetAttribute(place_list_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+  for (int j = 0; j < kNumTileSizes; ++j) {
+    CK(cudaFuncSetAttribute(kListKernels[j][0], cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CK(cudaFuncSetAttribute(kListKernels[j][1], cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+  }
   *out = ctx;
   return FL_OK;
 }
@@ -241,7 +252,7 @@ extern "C" int fl_ctx_destroy(fl_ctx *ctx) {
   }
   release_pop(ctx->pop);
   release_pop(ctx->scratch_pop);
-  DevBuf *bufs[] = {&ctx->tables, &ctx->err_flag, &ctx->con_begin, &ctx->org_list, &ctx->gaps, &ctx->rsc, &ctx->csc, &ctx->fit_out, &ctx->fit_scratch, &ctx->fb_count, &ctx->fb_pairs, &ctx->fast_scratch, &ctx->fb_total, &ctx->work_counters};
+  DevBuf *bufs[] = {&ctx->tables, &ctx->err_flag, &ctx->con_begin, &ctx->org_list, &ctx->gaps, &ctx->rsc, &ctx->csc, &ctx->fit_out, &ctx->fit_scratch, &ctx->fb_item_count, &ctx->fb_item_seqs, &ctx->fast_scratch, &ctx->fb_total, &ctx->work_counters};
   for (DevBuf *b : bufs) b->release();
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -476,9 +487,10 @@ static int upload_population(fl_ctx *ctx, Population &P, const fl_population *po
   if (n_org) CK(cudaMemcpyAsync(P.d_con_M.p, pop->con_M, (size_t)n_org * 4, cudaMemcpyHostToDevice, st));
   if (pop->n_con) CK(cudaMemcpyAsync(P.d_con_pool.p, pop->con_pool, (size_t)pop->n_con * 8, cudaMemcpyHostToDevice, st));
   if (n_org) CK(cudaMemcpyAsync(P.d_sum_len.p, P.sum_len.data(), (size_t)n_org * 4, cudaMemcpyHostToDevice, st));
-  // the caller may free its arrays as soon as we return
-  if (is_pinned(pop->con_pool) || is_pinned(pop->rec_pool) || is_pinned(pop->rec_begin) || is_pinned(pop->rec_data) || is_pinned(pop->edges_pool))
-    CK(cudaStreamSynchronize(st));
+  // the caller may free its arrays as soon as we return: copies from pageable memory are staged before
+  // cudaMemcpyAsync returns, copies from pinned memory are not -- rather than classify sixteen pointers, wait for
+  // the (small) uploads
+  CK(cudaStreamSynchronize(st));
   P.valid = true;
   return FL_OK;
 }
@@ -532,8 +544,10 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
         const long long cb = con_begin[(size_t)c * n_org + o];
         if (cb < 0 || cb + (long long)(n - 1) * (2LL * P.con_M[o] + 2) > P.n_con)
           return fail(FL_E_ARG, "con_begin[class %d][organism %d] points outside con_pool", c, o);
+        // only organisms with a connector read DEN_EXPANSION (connector.c:51-56); a single recognizer is placed on
+        // any sequence length, as in the reference
+        if (S - P.sum_len[o] + n > 10000) return fail(FL_E_UNSUPPORTED, "effective length %d exceeds DEN_EXPANSION (10000 entries, _constants.h:11)", S - P.sum_len[o] + n);
       }
-      if (S - P.sum_len[o] + n > 10000) return fail(FL_E_UNSUPPORTED, "effective length %d exceeds DEN_EXPANSION (10000 entries, _constants.h:11)", S - P.sum_len[o] + n);
     }
   }
   int rc;
@@ -548,6 +562,7 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
     CK(cudaMemsetAsync(ctx->csc.p, 0, cells * 8, ctx->stream));
   }
   CK(cudaMemcpyAsync(ctx->con_begin.p, con_begin, (size_t)n_cls * n_org * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (is_pinned(con_begin)) CK(cudaStreamSynchronize(ctx->stream));  // a pinned source is read asynchronously
 
   int n_sm = 148;
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
@@ -735,56 +750,92 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
       ctx->launches++;
     }
     if (n_fast_org > 0) {
-      const long long cap = n_fast_org * cl.count;
-      ctx->fast_pairs += cap;
-      if ((rc = ctx->fb_pairs.ensure((size_t)cap * sizeof(int2)))) return rc;
-      fp.fb_count = ctx->fb_count.as<int>();
-      fp.fb_pairs = ctx->fb_pairs.as<int2>();
-      if (cap > 0x7fffffffLL) return fail(FL_E_UNSUPPORTED, "%lld pairs in one length class exceed the hand-back list (2^31-1); split the population or the set", cap);
-      fp.fb_cap = (int)cap;
-      CK(cudaMemsetAsync(ctx->fb_count.p, 0, sizeof(int), ctx->stream));
+      ctx->fast_pairs += n_fast_org * cl.count;
+      // geometry of every bucket first, so that the hand-back lists can be sized before anything is launched
+      struct Geo {
+        int j, spc, chunks, per_round, n_b;
+        long long items, grid;
+      };
+      std::vector<Geo> geo;
+      ListBuckets lb;
+      lb.n = 0;
+      lb.item_begin[0] = 0;
+      long long pair_slots = 0, scratch_ints = 0;
       for (int j = 0; j < kNumFastConfigs; ++j) {
         const int n_b = (int)fast_bucket[j].size();
         if (!n_b) continue;
+        if (lb.n >= kMaxListBuckets) return fail(FL_E_UNSUPPORTED, "too many tile buckets");
         const int team = kFastConfigs[j].team, nt = 32 / team, nw = fast_warps[j];
+        Geo g;
+        g.j = j;
+        g.n_b = n_b;
+        g.per_round = nw * nt;
+        const long long pairs = (long long)n_b * cl.count;
+        const long long fast_target = (long long)n_sm * fast_ctas_per_sm[j] * 6;
+        int spc = (int)std::max<long long>(g.per_round, (pairs + fast_target - 1) / fast_target);
+        spc = std::min(spc, std::max(g.per_round, getenv("FLEMINGO_FAST_SPC") ? atoi(getenv("FLEMINGO_FAST_SPC")) : 256));
+        spc = ((spc + g.per_round - 1) / g.per_round) * g.per_round;
+        g.spc = spc;
+        g.chunks = (cl.count + spc - 1) / spc;
+        g.items = (long long)n_b * g.chunks;
+        g.grid = std::min<long long>(g.items, (long long)n_sm * fast_ctas_per_sm[j]);
+        if (lb.item_begin[lb.n] + g.items > 0x7fffffffLL) return fail(FL_E_UNSUPPORTED, "too many work items");
+        lb.chunks[lb.n] = g.chunks;
+        lb.spc[lb.n] = spc;
+        lb.org_begin[lb.n] = fast_begin[j];
+        lb.pair_base[lb.n] = pair_slots;
+        lb.item_begin[lb.n + 1] = lb.item_begin[lb.n] + (int)g.items;
+        ++lb.n;
+        pair_slots += g.items * spc;
+        scratch_ints = std::max(scratch_ints, g.grid * g.per_round * (long long)P.max_rec * fast_rowq[j]);
+        geo.push_back(g);
+      }
+      const int total_items = lb.item_begin[lb.n];
+      if ((rc = ctx->fb_item_count.ensure((size_t)total_items * 4 + 4)) || (rc = ctx->fb_item_seqs.ensure((size_t)pair_slots * 4 + 4)) ||
+          (rc = ctx->fast_scratch.ensure((size_t)scratch_ints * 4)))
+        return rc;
+      CK(cudaMemsetAsync(ctx->fb_item_count.p, 0, (size_t)total_items * 4, ctx->stream));
+      fp.fb_item_count = ctx->fb_item_count.as<int>();
+      fp.fb_item_seqs = ctx->fb_item_seqs.as<int>();
+      fp.scratch = ctx->fast_scratch.as<int>();
+      for (size_t b = 0; b < geo.size(); ++b) {
+        const Geo &g = geo[b];
+        const int j = g.j, nw = fast_warps[j];
         fp.rowq_stride = fast_rowq[j];
         fp.slotq_stride = fast_slot[j];
         fp.single_row = fast_single[j] ? 1 : 0;
         fp.scratch_slot_stride = (long long)P.max_rec * fast_rowq[j];
-        const int per_round = nw * nt;
-        const long long pairs = (long long)n_b * cl.count;
-        const long long fast_target = (long long)n_sm * fast_ctas_per_sm[j] * 6;
-        int spc = (int)std::max<long long>(per_round, (pairs + fast_target - 1) / fast_target);
-        spc = std::min(spc, std::max(per_round, getenv("FLEMINGO_FAST_SPC") ? atoi(getenv("FLEMINGO_FAST_SPC")) : 256));
-        spc = ((spc + per_round - 1) / per_round) * per_round;
         fp.base = pp;
         fp.base.org_list = d_list + fast_begin[j];
-        fp.base.seqs_per_cta = spc;
-        fp.base.chunks = (cl.count + spc - 1) / spc;
-        const long long items = (long long)n_b * fp.base.chunks;
-        if (items > 0x7fffffffLL) return fail(FL_E_UNSUPPORTED, "too many work items");
-        const long long grid = std::min<long long>(items, (long long)n_sm * fast_ctas_per_sm[j]);
-        if ((rc = ctx->fast_scratch.ensure((size_t)grid * per_round * (size_t)fp.scratch_slot_stride * 4))) return rc;
-        fp.scratch = ctx->fast_scratch.as<int>();
-        fp.n_items = (int)items;
+        fp.base.seqs_per_cta = g.spc;
+        fp.base.chunks = g.chunks;
+        fp.n_items = (int)g.items;
+        fp.item_base = lb.item_begin[b];
+        fp.pair_base = lb.pair_base[b];
         fp.work_counter = ctx->work_counters.as<int>() + (ctx->launches % 1024);
         CK(cudaMemsetAsync(fp.work_counter, 0, sizeof(int), ctx->stream));
         if (getenv("FLEMINGO_DEBUG_LAUNCH"))
-          fprintf(stderr, "fast launch: cfg J=%d team=%d warps=%d ctas/sm=%d grid=%lld items=%lld spc=%d smem=%zu rows=%d\n", kFastConfigs[j].J, team, nw,
-                  fast_ctas_per_sm[j], grid, items, spc, fast_smem[j], fast_single[j] ? 1 : 2);
-        kFastConfigs[j].fn<<<(unsigned)grid, nw * 32, fast_smem[j], ctx->stream>>>(fp);
+          fprintf(stderr, "fast launch: cfg J=%d team=%d warps=%d ctas/sm=%d grid=%lld items=%lld spc=%d smem=%zu rows=%d\n", kFastConfigs[j].J,
+                  kFastConfigs[j].team, nw, fast_ctas_per_sm[j], g.grid, g.items, g.spc, fast_smem[j], fast_single[j] ? 1 : 2);
+        kFastConfigs[j].fn<<<(unsigned)g.grid, nw * 32, fast_smem[j], ctx->stream>>>(fp);
         CK(cudaGetLastError());
         ctx->launches++;
       }
-      // the pairs the integer pass declined, by the exact kernel in list mode (one warp per CTA)
+      // the pairs the integer pass declined, by the exact kernel in list mode: one organism prologue per work item that
+      // has hand-backs, the item's pairs spread over the warps of the CTA
       PlaceParams lp = pp;
-      const size_t lsmem = 8ull * ((size_t)lp.pool_stride + (size_t)(P.max_rec - 1) * lp.g_stride + (size_t)lp.nrows * lp.row_stride) +
-                           sizeof(RecDesc) * P.max_rec + (size_t)lp.code_stride;
-      const unsigned lgrid = (unsigned)std::min<long long>(cap, (long long)n_sm * 16);
-      if (trace)
-        place_list_kernel<true><<<lgrid, 32, lsmem, ctx->stream>>>(lp, fp.fb_count, fp.fb_pairs, ctx->fb_total.as<unsigned long long>());
-      else
-        place_list_kernel<false><<<lgrid, 32, lsmem, ctx->stream>>>(lp, fp.fb_count, fp.fb_pairs, ctx->fb_total.as<unsigned long long>());
+      lp.org_list = d_list;
+      int lw = 4;
+      size_t lsmem = 0;
+      for (;; lw >>= 1) {
+        lsmem = 8ull * ((size_t)lp.pool_stride + (size_t)(P.max_rec - 1) * lp.g_stride + (size_t)lw * lp.nrows * lp.row_stride) +
+                sizeof(RecDesc) * P.max_rec + (size_t)lw * lp.code_stride;
+        if (lsmem <= (size_t)kMaxSmem / 2 || lw == 1) break;
+      }
+      if (lsmem > (size_t)kMaxSmem) return fail(FL_E_UNSUPPORTED, "list-mode placement needs %zu bytes of shared memory (limit %d)", lsmem, kMaxSmem);
+      const unsigned lgrid = (unsigned)std::min<long long>(((long long)total_items + 31) / 32, (long long)n_sm * 4);
+      kListKernels[pick_tile(Pmax)][trace ? 1 : 0]<<<lgrid, lw * 32, lsmem, ctx->stream>>>(lp, lb, fp.fb_item_count, fp.fb_item_seqs,
+                                                                                          ctx->fb_total.as<unsigned long long>());
       CK(cudaGetLastError());
       ctx->launches++;
     }
@@ -853,14 +904,20 @@ extern "C" int fl_path_stats(fl_ctx *ctx, long long *fast_pairs, long long *fall
   return FL_OK;
 }
 
-extern "C" int fl_fitness(fl_ctx *ctx, int pos_set, int neg_set, int method, double gamma, double *out) {
-  if (!ctx || !out) return fail(FL_E_ARG, "fl_fitness: null argument");
+// Launches the fitness reduction of the resident energies into ctx->fit_out ([max(n_org, pad_rows)][5], rows beyond
+// n_org zeroed).  Asynchronous.
+static int fitness_launch(fl_ctx *ctx, int pos_set, int neg_set, int method, double gamma, int pad_rows, int *n_org_out) {
   if (pos_set < 0 || pos_set >= FL_MAX_SETS || neg_set < 0 || neg_set >= FL_MAX_SETS) return fail(FL_E_ARG, "fl_fitness: set id out of range");
   if (method < FL_FIT_WELCH || method > FL_FIT_TRIM_LEFT_M_SD) return fail(FL_E_ARG, "fl_fitness: unknown method %d", method);
   CK(cudaSetDevice(ctx->device));
   SeqSet &sp = ctx->sets[pos_set], &sn = ctx->sets[neg_set];
   if (!sp.E_valid || !sn.E_valid || sp.E_n_org != sn.E_n_org) return fail(FL_E_STATE, "fl_fitness: energies of both sets must be computed (fl_place_batch) for the current population");
   const int n_org = sp.E_n_org;
+  *n_org_out = n_org;
+  const int rows = std::max(n_org, pad_rows);
+  int rc;
+  if ((rc = ctx->fit_out.ensure((size_t)std::max(rows, 1) * 5 * 8))) return rc;
+  if (rows > n_org) CK(cudaMemsetAsync(ctx->fit_out.as<double>() + (size_t)n_org * 5, 0, (size_t)(rows - n_org) * 5 * 8, ctx->stream));
   if (n_org == 0) return FL_OK;
   if (sp.n_seq < 1 || sn.n_seq < 1) return fail(FL_E_ARG, "fl_fitness: empty sequence set");
   // n_to_trim = round(gamma * N): python rounds half to even (organism_object.py:892), as nearbyint does
@@ -869,15 +926,32 @@ extern "C" int fl_fitness(fl_ctx *ctx, int pos_set, int neg_set, int method, dou
   int n2 = 1;
   while (n2 < std::max(sp.n_seq, sn.n_seq)) n2 <<= 1;
   const bool need_sort = method != FL_FIT_WELCH && (trim_p != 0 || trim_n != 0);
-  int rc;
-  if ((rc = ctx->fit_out.ensure((size_t)n_org * 5 * 8))) return rc;
   if (need_sort && (rc = ctx->fit_scratch.ensure((size_t)n_org * n2 * 8))) return rc;
   fitness_kernel<<<n_org, 256, 0, ctx->stream>>>(sp.E.as<double>(), sp.n_seq, sn.E.as<double>(), sn.n_seq, method, trim_p, trim_n,
                                                  ctx->fit_scratch.as<double>(), n2, ctx->fit_out.as<double>());
   CK(cudaGetLastError());
   ctx->launches++;
+  return FL_OK;
+}
+
+extern "C" int fl_fitness(fl_ctx *ctx, int pos_set, int neg_set, int method, double gamma, double *out) {
+  if (!ctx || !out) return fail(FL_E_ARG, "fl_fitness: null argument");
+  int n_org = 0;
+  const int rc = fitness_launch(ctx, pos_set, neg_set, method, gamma, 0, &n_org);
+  if (rc) return rc;
+  if (n_org == 0) return FL_OK;
   CK(cudaMemcpyAsync(out, ctx->fit_out.p, (size_t)n_org * 5 * 8, cudaMemcpyDeviceToHost, ctx->stream));
   return check_device_errors(ctx);
+}
+
+extern "C" int fl_fitness_dev(fl_ctx *ctx, int pos_set, int neg_set, int method, double gamma, int pad_rows, void **out_dev) {
+  if (!ctx || !out_dev) return fail(FL_E_ARG, "fl_fitness_dev: null argument");
+  if (pad_rows < 0) return fail(FL_E_ARG, "fl_fitness_dev: negative pad_rows");
+  int n_org = 0;
+  const int rc = fitness_launch(ctx, pos_set, neg_set, method, gamma, pad_rows, &n_org);
+  if (rc) return rc;
+  *out_dev = ctx->fit_out.p;
+  return FL_OK;
 }
 
 extern "C" int fl_calculate(fl_ctx *ctx, const char *sequence, int seq_len, const char *rec_types, int n_rec,
@@ -969,5 +1043,80 @@ extern "C" int fl_calculate(fl_ctx *ctx, const char *sequence, int seq_len, cons
     if (i + 1 < n_rec) con_scores[i] = csc[i];
   }
   rec_scores[n_rec] = energy;
+  return FL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Roofline denominator, measured where the bench runs: the issue rate of the instruction the DP stage is made of
+// (VIADDMNMX, max(a + b, c) in one instruction; 8 independent chains per thread, no memory traffic).
+// ------------------------------------------------------------------------------------------------
+template <bool PACKED16>
+__global__ void __launch_bounds__(256) dpx_rate_kernel(int *out, const int *in, int iters) {
+  constexpr int ACC = 8;
+  int acc[ACC], g[ACC];
+#pragma unroll
+  for (int a = 0; a < ACC; ++a) {
+    acc[a] = in[threadIdx.x + a * 256];
+    g[a] = in[threadIdx.x + 2048 + a * 256];
+  }
+  int p = in[4096 + (threadIdx.x & 31)];
+  const int dp = in[4200];
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int a = 0; a < ACC; ++a)
+        acc[a] = PACKED16 ? (int)__viaddmax_s16x2((unsigned)p, (unsigned)g[a], (unsigned)acc[a]) : __viaddmax_s32(p, g[a], acc[a]);
+      p += dp;
+    }
+  }
+  int r = acc[0];
+#pragma unroll
+  for (int a = 1; a < ACC; ++a) r += acc[a];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+extern "C" int fl_measure_dpx_rate(fl_ctx *ctx, double *cells_per_s_i32, double *cells_per_s_i16x2, int *n_sm, int *sm_clock_khz) {
+  if (!ctx) return fail(FL_E_ARG, "fl_measure_dpx_rate: null context");
+  CK(cudaSetDevice(ctx->device));
+  int sms = 0, khz = 0;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+  CK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device));
+  const int blocks = sms * 8, iters = 2048;
+  DevBuf in, out;
+  int rc;
+  if ((rc = in.ensure(8192 * 4)) || (rc = out.ensure((size_t)blocks * 256 * 4))) return rc;
+  std::vector<int> h(8192);
+  for (int i = 0; i < 8192; ++i) h[i] = -(i % 97) * 37 - 1;
+  CK(cudaMemcpyAsync(in.p, h.data(), 8192 * 4, cudaMemcpyHostToDevice, ctx->stream));
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  double rate[2] = {0, 0};
+  for (int v = 0; v < 2; ++v) {
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {  // the first repetition warms up
+      CK(cudaEventRecord(a, ctx->stream));
+      if (v == 0)
+        dpx_rate_kernel<false><<<blocks, 256, 0, ctx->stream>>>(out.as<int>(), in.as<int>(), iters);
+      else
+        dpx_rate_kernel<true><<<blocks, 256, 0, ctx->stream>>>(out.as<int>(), in.as<int>(), iters);
+      CK(cudaEventRecord(b, ctx->stream));
+      CK(cudaEventSynchronize(b));
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, a, b));
+      if (rep > 0 && ms < best) best = ms;
+    }
+    const double cells = (double)blocks * 256 * 4.0 * 8 * iters * (v == 1 ? 2.0 : 1.0);
+    rate[v] = cells / (best * 1e-3);
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  in.release();
+  out.release();
+  if (cells_per_s_i32) *cells_per_s_i32 = rate[0];
+  if (cells_per_s_i16x2) *cells_per_s_i16x2 = rate[1];
+  if (n_sm) *n_sm = sms;
+  if (sm_clock_khz) *sm_clock_khz = khz;
   return FL_OK;
 }

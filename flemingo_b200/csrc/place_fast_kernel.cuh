@@ -28,9 +28,12 @@ constexpr int kSlackUnits = 2; // covers fp64-vs-real rounding of the reference 
 struct FastParams {
   PlaceParams base;
   const unsigned char *has_unk;  // [n_seq] sequence holds a non-ACGT byte -> exact kernel
-  int *fb_count;
-  int2 *fb_pairs;
-  int fb_cap;
+  // hand-back lists, one per work item (organism x chunk of sequences), so that the exact list kernel meets the pairs
+  // already grouped by organism: item g = item_base + item owns fb_item_seqs[pair_base + item * seqs_per_cta ...]
+  int *fb_item_count;
+  int *fb_item_seqs;
+  int item_base;
+  long long pair_base;
   int gq_stride;     // ints per quantised connector table (kGPad + Pmax + kGPad)
   int rowq_stride;   // ints per quantised row
   int slotq_stride;  // ints per pair slot (1 or 2 rows), == TEAM (mod 32) so that teams hit disjoint banks
@@ -907,8 +910,8 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
           if (r_live[t] && (!r_active[t] || r_failed[t])) {
-            const int idx = atomicAdd(f.fb_count, 1);
-            if (idx < f.fb_cap) f.fb_pairs[idx] = make_int2(v.o, r_seq[t]);
+            const int idx = atomicAdd(f.fb_item_count + f.item_base + item, 1);  // < seqs_per_cta: a pair is handed back once
+            f.fb_item_seqs[f.pair_base + (long long)item * p.seqs_per_cta + idx] = r_seq[t];
           }
         }
       }

@@ -440,7 +440,9 @@ __device__ __forceinline__ void place_pair_exact(const PlaceParams &p, const Org
       int found = -1;
       for (int kb = 0; kb <= m && found < 0; kb += 32) {
         const int k = kb + lane;
-        const bool hit = (k <= m) && ((prev[k] + Gc[m - k]) + ri == target);
+        // target == -inf (e.g. a -inf PSSM entry on the path): the reference's strict '<' never fires from its -inf
+        // start value, so nothing "won" and its calloc'ed zeros stay (organism.c:365)
+        const bool hit = (k <= m) && (target > neg_inf()) && ((prev[k] + Gc[m - k]) + ri == target);
         const unsigned bal = __ballot_sync(0xffffffffu, hit);
         if (bal) found = kb + __ffs(bal) - 1;
       }
@@ -500,22 +502,50 @@ __global__ void __launch_bounds__(256) place_tiled_kernel(const PlaceParams p) {
 
 // ------------------------------------------------------------------------------------------------
 // List mode: the pairs the integer fast path declined (too many near-ties, unknown bytes, tables that do
-// not fit its fixed-point range).  One warp per CTA, grid-stride over the device-side list.
+// not fit its fixed-point range).  The fast kernel files them per work item (organism x chunk of sequences), so
+// a CTA here claims an item that has hand-backs, runs the organism prologue ONCE and lets its warps take the
+// item's pairs in turn.  Items are scanned 32 at a time (one count per lane + ballot).
 // ------------------------------------------------------------------------------------------------
-template <bool TRACE>
-__global__ void __launch_bounds__(32) place_list_kernel(const PlaceParams p, const int *__restrict__ fb_count,
-                                                        const int2 *__restrict__ fb_pairs, unsigned long long *fb_total) {
+constexpr int kMaxListBuckets = 24;
+struct ListBuckets {
+  int n;                                  // fast-path launches (tile buckets) of this length class
+  int item_begin[kMaxListBuckets + 1];    // first global item of bucket b; [n] = total
+  int chunks[kMaxListBuckets];            // chunks per organism
+  int spc[kMaxListBuckets];               // sequences per chunk = slots per item in fb_item_seqs
+  int org_begin[kMaxListBuckets];         // first entry of the bucket in p.org_list
+  long long pair_base[kMaxListBuckets];   // first slot of the bucket in fb_item_seqs
+};
+
+template <int J, bool TRACE>
+__global__ void __launch_bounds__(128) place_list_kernel(const PlaceParams p, const ListBuckets lb, const int *__restrict__ fb_item_count,
+                                                         const int *__restrict__ fb_item_seqs, unsigned long long *fb_total) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const ExactSmem sm = carve_exact(p, smem_raw, 1);
-  const int count = *fb_count;
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(fb_total, (unsigned long long)count);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const ExactSmem sm = carve_exact(p, smem_raw, nwarps);
+  double *rows = sm.rows + (size_t)warp * p.nrows * p.row_stride;
+  unsigned char *codes = sm.codes + (size_t)warp * p.code_stride;
+  const int total = lb.item_begin[lb.n];
   int err = 0;
-  for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
-    const int2 pr = fb_pairs[idx];
-    __syncthreads();
-    const OrgView v = organism_prologue(p, pr.x, sm.pool, sm.G, sm.rec);
-    __syncthreads();
-    place_pair_exact<5, TRACE>(p, v, pr.y, sm.pool, sm.G, sm.rec, sm.rows, sm.codes, threadIdx.x, err);
+  for (int g0 = blockIdx.x * 32; g0 < total; g0 += gridDim.x * 32) {
+    const int c = (g0 + lane < total) ? __ldg(fb_item_count + g0 + lane) : 0;
+    unsigned todo = __ballot_sync(0xffffffffu, c > 0);  // the same mask in every warp of the CTA
+    while (todo) {
+      const int bit = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int g = g0 + bit;
+      const int cnt = __shfl_sync(0xffffffffu, c, bit);
+      int b = 0;
+      while (b + 1 < lb.n && lb.item_begin[b + 1] <= g) ++b;
+      const int item = g - lb.item_begin[b];
+      const int oi = item / lb.chunks[b];
+      const int *seqs = fb_item_seqs + lb.pair_base[b] + (long long)item * lb.spc[b];
+      if (threadIdx.x == 0) atomicAdd(fb_total, (unsigned long long)cnt);
+      __syncthreads();  // the previous item's tables are dead
+      const OrgView v = organism_prologue(p, p.org_list[lb.org_begin[b] + oi], sm.pool, sm.G, sm.rec);
+      __syncthreads();
+      for (int i = warp; i < cnt; i += nwarps)
+        place_pair_exact<J, TRACE>(p, v, __ldg(seqs + i), sm.pool, sm.G, sm.rec, rows, codes, lane, err);
+    }
   }
   if (err) atomicOr(p.err_flag, err);
 }

@@ -69,12 +69,76 @@ def gather_stats(local_stats: np.ndarray, shards: list, rank: int, world_size: i
     return full
 
 
+class DeviceGather:
+    """The one collective of the multi-GPU path, without host hops: every rank's [width, 5] block of statistics is
+    all-gathered straight out of the library's device buffer (Engine.fitness_dev) on the engine's own stream, and the
+    gathered [world, width, 5] array comes back to the host in ONE copy through a pinned buffer.
+
+    Replaces the reference's comm.gather of pickled organisms / fitness lists (src/search_organisms.py:268-277).
+    """
+
+    def __init__(self, engine, shards: list, rank: int, world_size: int, device, group=None):
+        import torch
+        self.engine, self.shards, self.rank, self.world, self.group = engine, shards, rank, world_size, group
+        self.device = device
+        self.width = max(1, max(len(s) for s in shards))
+        self.n_org = int(sum(len(s) for s in shards))
+        self.stream = torch.cuda.ExternalStream(engine.stream_handle, device=device)
+        self.gathered = torch.empty((world_size * self.width, 5), dtype=torch.float64, device=device)
+        self.host = torch.empty((world_size * self.width, 5), dtype=torch.float64).pin_memory()
+        self._view, self._view_key = None, None
+        # scatter map: row of the gathered array -> organism index
+        self._rows = np.concatenate([r * self.width + np.arange(len(s)) for r, s in enumerate(shards)]) if self.n_org else np.zeros(0, np.int64)
+        self._orgs = np.concatenate([np.asarray(s, dtype=np.int64) for s in shards]) if self.n_org else np.zeros(0, np.int64)
+
+    def __call__(self, pos, neg, method: str = "Welch", gamma: float = 0.2, empty: bool = False) -> np.ndarray:
+        """fitness reduction of this rank's organisms + all-gather; returns the full [n_org, 5] array on every rank.
+        empty=True: this rank owns no organism (more ranks than organisms) and contributes a block of zeros."""
+        import torch
+        import torch.distributed as dist
+        stats = None if empty else self.engine.fitness_dev(pos, neg, method, gamma, pad_rows=self.width)
+        with torch.cuda.stream(self.stream):
+            if empty:
+                block = torch.zeros((self.width, 5), dtype=torch.float64, device=self.device)
+            else:
+                key = (stats.ptr, stats.rows)
+                if self._view_key != key:   # the library's buffer only moves when it grows
+                    self._view, self._view_key = torch.as_tensor(stats, device=self.device), key
+                block = self._view[: self.width]
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.gathered, block, group=self.group)
+                self.host.copy_(self.gathered, non_blocking=True)
+            else:
+                self.host[: self.width].copy_(block, non_blocking=True)
+        self.stream.synchronize()
+        self.engine.sync()          # surfaces device-side errors (NaN null bin) like fl_fitness does
+        full = np.empty((self.n_org, 5))
+        full[self._orgs] = self.host.numpy()[self._rows]
+        return full
+
+
 def evaluate_sharded(engine, organisms, pos_sequences, neg_sequences, method: str = "Welch", gamma: float = 0.2,
-                     rank: int = 0, world_size: int = 1, device=None, group=None, shards=None) -> np.ndarray:
-    """Fitness statistics [n_org, 5] of the WHOLE population on every rank; this rank places only its shard."""
+                     rank: int = 0, world_size: int = 1, device=None, group=None, shards=None, reuse_sets: bool = True,
+                     gather: "DeviceGather | None" = None) -> np.ndarray:
+    """Fitness statistics [n_org, 5] of the WHOLE population on every rank; this rank places only its shard.
+
+    On a CUDA device the statistics never visit the host before the collective (DeviceGather); with device=None
+    (gloo, CPU tests with a stand-in engine) they go through gather_stats."""
     if shards is None:
         seq_len = max((len(s) for s in pos_sequences), default=1)
         shards = shard_by_cost(organism_costs(organisms, seq_len), world_size)
     mine = [organisms[i] for i in shards[rank]]
-    local = engine.evaluate(mine, pos_sequences, neg_sequences, method, gamma) if mine else np.zeros((0, 5))
-    return gather_stats(local, shards, rank, world_size, device, group)
+    on_gpu = device is not None and getattr(device, "type", "cpu") == "cuda"
+    if not on_gpu:
+        local = engine.evaluate(mine, pos_sequences, neg_sequences, method, gamma) if mine else np.zeros((0, 5))
+        return gather_stats(local, shards, rank, world_size, device, group)
+    if gather is None:
+        gather = DeviceGather(engine, shards, rank, world_size, device, group)
+    # sequences first: their copies and the packing kernel run while the host packs the population
+    pos = engine.upload_sequences(pos_sequences, 0, reuse=reuse_sets)
+    neg = engine.upload_sequences(neg_sequences, 1, reuse=reuse_sets)
+    if mine:
+        engine.upload_population(mine)
+        engine.place(pos, fetch=False)
+        engine.place(neg, fetch=False)
+    return gather(pos, neg, method, gamma, empty=not mine)

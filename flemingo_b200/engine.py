@@ -43,6 +43,19 @@ class PlacementBatch:
     con_scores: np.ndarray | None = None
 
 
+class DeviceStats:
+    """A [rows, 5] float64 array in device memory owned by the library (valid until the next fitness call)."""
+
+    def __init__(self, ptr: int, rows: int, n_org: int, stream: int):
+        self.ptr, self.rows, self.n_org, self.stream = ptr, rows, n_org, stream
+
+    @property
+    def __cuda_array_interface__(self):
+        # no "stream" entry: consumers would synchronise with it on import; callers order their work by running on
+        # Engine.stream_handle (self.stream) instead
+        return {"shape": (self.rows, 5), "typestr": "<f8", "data": (self.ptr, False), "version": 2, "strides": None}
+
+
 class Engine:
     def __init__(self, device: int | None = None):
         self._lib = _cabi.load_library()
@@ -54,6 +67,7 @@ class Engine:
         _cabi.check(self._lib.fl_ctx_create(device, _ptr(tables), tables.size, C.byref(handle)))
         self._ctx = handle
         self._packed: PackedPopulation | None = None
+        self._uploaded_con_size = -1
         self._sets: dict[int, SequenceSet] = {}
         # True: skip the integer filter pass and place every pair with the exact fp64 kernel (same results)
         self.exact_only = os.environ.get("FLEMINGO_EXACT_ONLY", "0") == "1"
@@ -84,6 +98,12 @@ class Engine:
         a, b = C.c_longlong(0), C.c_longlong(0)
         _cabi.check(self._lib.fl_path_stats(self._ctx, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
+
+    def measure_dpx_rate(self) -> dict:
+        """DP cells per second the DPX instruction of the DP stage can issue on this device (fl_measure_dpx_rate)."""
+        a, b, n, k = C.c_double(0), C.c_double(0), C.c_int(0), C.c_int(0)
+        _cabi.check(self._lib.fl_measure_dpx_rate(self._ctx, C.byref(a), C.byref(b), C.byref(n), C.byref(k)))
+        return {"cells_per_s_i32": a.value, "cells_per_s_i16x2": b.value, "n_sm": n.value, "sm_clock_khz": k.value}
 
     def sync(self):
         _cabi.check(self._lib.fl_sync(self._ctx))
@@ -145,7 +165,7 @@ class Engine:
         pop.edges_pool = _ptr(packed.edges_pool)
         pop.n_edges = int(packed.edges_pool.size)
         _cabi.check(self._lib.fl_upload_population(self._ctx, C.byref(pop)))
-        packed.uploaded_con_size = int(packed.con_pool.size)
+        self._uploaded_con_size = int(packed.con_pool.size)   # per engine: one packed population may feed several GPUs
         self._packed = packed
 
     # -- batched placement ----------------------------------------------------------------------
@@ -160,10 +180,10 @@ class Engine:
         sset = self._sets[seqset] if isinstance(seqset, int) else seqset
         packed = self._packed
         con_begin = packed.con_begin_for_lengths(sset.class_len)
-        if packed.con_pool.size != packed.uploaded_con_size:
+        if packed.con_pool.size != self._uploaded_con_size:
             # a rescaled connector variant was appended (rare): grow the device pool, keep resident energies
             _cabi.check(self._lib.fl_update_connectors(self._ctx, _ptr(packed.con_pool), int(packed.con_pool.size)))
-            packed.uploaded_con_size = int(packed.con_pool.size)
+            self._uploaded_con_size = int(packed.con_pool.size)
         n_org, n_seq, mr = packed.n_org, sset.n_seq, packed.max_rec
         energies = gaps = rsc = csc = None
         if fetch:
@@ -190,6 +210,20 @@ class Engine:
         out = np.empty((self._packed.n_org, 5), dtype=np.float64)
         _cabi.check(self._lib.fl_fitness(self._ctx, ps, ns, _cabi.FIT_METHODS[method], float(gamma), _ptr(out)))
         return out
+
+    def fitness_dev(self, pos: SequenceSet | int, neg: SequenceSet | int, method: str = "Welch", gamma: float = 0.2,
+                    pad_rows: int = 0) -> "DeviceStats":
+        """Same reduction, but the [max(n_org, pad_rows), 5] statistics stay in HBM (fl_fitness_dev): no copy, no
+        synchronisation.  The result exposes __cuda_array_interface__, so `torch.as_tensor(stats, device=...)` is a
+        zero-copy view -- the send buffer of the multi-GPU all-gather (flemingo_b200.distributed)."""
+        if method not in _cabi.FIT_METHODS:
+            raise ValueError('Unknown method "' + str(method) + '". Please check ' +
+                             'the FITNESS_FUNCTION paramter in the config file.')
+        ps = pos if isinstance(pos, int) else pos.set_id
+        ns = neg if isinstance(neg, int) else neg.set_id
+        ptr = C.c_void_p()
+        _cabi.check(self._lib.fl_fitness_dev(self._ctx, ps, ns, _cabi.FIT_METHODS[method], float(gamma), int(pad_rows), C.byref(ptr)))
+        return DeviceStats(int(ptr.value or 0), max(self._packed.n_org, int(pad_rows)), self._packed.n_org, self.stream_handle)
 
     def evaluate(self, organisms, pos_sequences, neg_sequences, method: str = "Welch", gamma: float = 0.2,
                  reuse_sets: bool = True) -> np.ndarray:

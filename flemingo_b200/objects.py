@@ -22,6 +22,7 @@ import math
 
 import numpy as np
 
+from . import builders
 from . import multiplacement as _multiplacement
 from .engine import get_engine
 from .population import rescale_connector_block
@@ -92,11 +93,10 @@ class PssmObject:
         self.recalculate_pssm()
 
     def recalculate_pssm(self) -> None:
-        # pssm_object.py:368-400: float(np.log2(...)) then python round to 2 decimals
-        cols = []
-        for column in self.pwm:
-            cols.append({b: round(float(np.log2(4.0 * column[b] + self.pseudo_count)), 2) for b in ("c", "t", "g", "a")})
-        self.pssm = np.array(cols)
+        # pssm_object.py:368-400: float(np.log2(4 p + pc)) rounded to 2 decimals with Python's round, per base
+        vals = builders.pssm_values(np.array([[column[b] for b in ("c", "t", "g", "a")] for column in self.pwm], dtype=np.float64),
+                                    self.pseudo_count)
+        self.pssm = np.array([{"c": float(r[0]), "t": float(r[1]), "g": float(r[2]), "a": float(r[3])} for r in vals])
 
     def get_type(self):
         return 'p'
@@ -148,18 +148,7 @@ class ShapeObject:
             self._mu = self.min_mu
         elif self._mu > self.max_mu:
             self._mu = self.max_mu
-        n_bins = len(self.edges) - 1
-        auc = norm_cdf(self.edges[-1], self._mu, self._sigma) - norm_cdf(self.edges[0], self._mu, self._sigma)
-        auc += n_bins * self.pseudo_count
-        log_auc = np.log(auc)
-        self.alt_model = []
-        for i in range(n_bins):
-            lo, hi = self.edges[i], self.edges[i + 1]
-            if self._sigma != 0:
-                mass = norm_cdf(hi, self._mu, self._sigma) - norm_cdf(lo, self._mu, self._sigma)
-            else:
-                mass = 1 if lo == self._mu else 0   # shape_object.py:21-36
-            self.alt_model.append(np.log(mass + self.pseudo_count) - log_auc)
+        self.alt_model = list(builders.shape_alt_models([self._mu], [self._sigma], [self.edges], self.pseudo_count)[0])
 
     def get_type(self):
         return self._TYPE_CHAR.get(self.type)
@@ -200,22 +189,11 @@ class ConnectorObject:
     def set_precomputed_pdfs_cdfs(self) -> None:
         # connector_object.py:175-206: pdf[d] = log2(Phi(d+.5) - Phi(d-.5) + pc),
         #                              cdf[d] = log2(Phi(d-.5) - Phi(-.5) + pc*(d+1))
-        # Phi is evaluated point by point with math.erf exactly as the reference does (norm_cdf, :19-30); the
-        # differences and logs are numpy vector operations on the same doubles in the same order, which is
-        # bit-identical to the reference's scalar loop (tests/test_oracle_golden.py) and ~10x faster.
-        n = self.max_seq_length
-        mu, sigma = self._mu, self._sigma
-        if sigma == 0:
-            phi = np.array([norm_cdf(d - 0.5, mu, sigma) for d in range(n + 1)], dtype=np.float64)
-        else:
-            scale, root2, erf = abs(sigma), math.sqrt(2.0), math.erf
-            phi = np.array([(1.0 + erf(((d - 0.5) - mu) / scale / root2)) / 2.0 for d in range(n + 1)], dtype=np.float64)
-        below, above = phi[:-1], phi[1:]
-        with np.errstate(divide="ignore", invalid="ignore"):
-            cdfs = np.log2(below - phi[0] + self.pseudo_count * np.arange(1, n + 1))
-            pdfs = np.log2(above - below + self.pseudo_count)
-        self.stored_pdfs = list(pdfs)
-        self.stored_cdfs = list(cdfs)
+        # Phi point by point with libm erf in the library (fl_build_connector_tables), log2 by numpy: bit-identical
+        # to the reference's scalar loop (tests/test_builders_cpu.py, golden flat arrays)
+        pdfs, cdfs = builders.connector_tables([self._mu], [self._sigma], self.max_seq_length, self.pseudo_count, n_threads=1)
+        self.stored_pdfs = list(pdfs[0])
+        self.stored_cdfs = list(cdfs[0])
 
     def adjust_scores(self, c_scores, sequence_length, sum_recognizer_lengths):
         rescale_connector_block(c_scores, self._mu, self._sigma, self.pseudo_count, self.max_seq_length,

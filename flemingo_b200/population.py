@@ -22,38 +22,42 @@ import numpy as np
 SHAPE_TYPES = "mtrh"
 
 
-def _g(x, mu, sigma):
-    # connector_object.py:15-16
-    return -(1 / 2) * ((x - mu) / sigma) ** 2
-
-
 def rescale_connector_block(block: np.ndarray, mu: float, sigma: float, pseudo_count: float, M: int,
                             sequence_length: int, sum_recognizer_lengths: int) -> None:
-    """In-place restatement of ConnectorObject.adjust_scores (connector_object.py:454-487).
+    """What ConnectorObject.adjust_scores (connector_object.py:454-487) writes, in closed form.
 
     `block` is the connector's [pdf[0..M) ++ cdf[0..M)] slice (the reference passes `c_scores[offset:]`).
-    Natural logs on purpose: that is what the reference writes (unlike the log2 tables of :175-206).
-    sigma == 0 raises ZeroDivisionError exactly as the reference does.
+    The reference re-normalises the Gaussian over the gaps 0..top (top = S - sum L) with sigma' = min(sigma, 1e-100).
+    It is only called when mu > S + 0.5, so every gap is at least 1.5 below mu and, with sigma' <= 1e-100, the ratio
+    of neighbouring weights is exp(-(2 (mu - x) - 1) / (2 sigma'^2)) <= exp(-1e200) = 0.0: all the mass sits on the
+    largest gap.  What is left is the pseudo count:
+
+        weight(top) = 1 + pc,  weight(x < top) = 0 + pc,  total = sequential sum in that order,
+        pdf[x] = ln(weight(x) / total),  cdf[x] = ln(running sum of the probabilities from gap 0 up)
+
+    (natural logs on purpose, unlike the log2 tables of :175-206).  The sums are accumulated in the reference's order
+    so the doubles are bit-identical (golden `rescale_*` cases).  sigma == 0 raises ZeroDivisionError as the reference
+    does; a sigma' so small that the exponent overflows makes the reference produce NaN everywhere, and so do we.
     """
     sigma = min(sigma, 1E-100)
     top = sequence_length - sum_recognizer_lengths
-    g_curr = _g(top, mu, sigma)
-    h_curr = 1
-    weights = [1 + pseudo_count]
-    total = weights[0]
-    for i in range(top - 1, -1, -1):
-        g_next = _g(i, mu, sigma)
-        h_next = h_curr * math.exp(g_next - g_curr)
-        weights.append(h_next + pseudo_count)
-        total += h_next + pseudo_count
-        g_curr = g_next
-        h_curr = h_next
-    probs = [h / total for h in reversed(weights)]
-    running = 0.0
-    for i, p in enumerate(probs):
-        running += p
-        block[i] = np.log(p)
-        block[M + i] = np.log(running)
+    if sigma == 0:
+        raise ZeroDivisionError("float division by zero")
+    n = top + 1
+    if not (float(sequence_length) + 0.5 < mu):
+        raise ValueError("adjust_scores is only defined for mu beyond the sequence (organism_object.py:1317)")
+    # the exponent of the gap farthest from mu, evaluated like the reference does (connector_object.py:15-16): a float
+    # power that overflows raises OverflowError there and here; an infinite quotient turns its weights into NaN
+    if not math.isfinite(-(1 / 2) * ((0 - mu) / sigma) ** 2):
+        block[:n] = np.nan
+        block[M:M + n] = np.nan
+        return
+    weights = np.full(n, 0.0 + pseudo_count)      # gap order 0..top
+    weights[top] = 1 + pseudo_count
+    total = np.add.accumulate(weights[::-1])[-1]  # the reference adds from the largest gap down
+    probs = weights / total
+    block[:n] = np.log(probs)
+    block[M:M + n] = np.log(np.add.accumulate(probs))
 
 
 @dataclass
@@ -83,7 +87,6 @@ class PackedPopulation:
     # (organism index, sequence length) -> offset of the rescaled variant in con_pool
     variants: dict = field(default_factory=dict)
     n_base_con: int = 0
-    uploaded_con_size: int = -1
     _con_org: np.ndarray = None
     _con_mu_pos: np.ndarray = None
 
@@ -267,6 +270,14 @@ def pack_population(organisms) -> PackedPopulation:
     firsts = [org.connectors[0] if m else None for org, m in zip(organisms, multi.tolist())]
     con_M = np.fromiter((f.max_seq_length if f is not None else 0 for f in firsts), dtype=np.int32, count=n_org)
     pcs = np.fromiter((f.pseudo_count if f is not None else 0.0 for f in firsts), dtype=np.float64, count=n_org)
+    # one table length and one pseudo count per organism: the reference takes both from each connector
+    # (organism_object.py:1303-1329), the packed layout from the first one -- refuse organisms where they differ
+    for org, f in zip(organisms, firsts):
+        if f is not None and len(org.connectors) > 1:
+            for c in org.connectors[1:]:
+                if c.max_seq_length != f.max_seq_length or c.pseudo_count != f.pseudo_count:
+                    raise ValueError(f"organism {getattr(org, '_id', '?')}: connectors with different max_seq_length / "
+                                     "pseudo_count in one organism are not supported")
     if bool(np.any(multi & (con_sizes != (n_rec - 1) * (2 * con_M.astype(np.int64) + 2)))):
         raise ValueError("connectors_scores_flat does not match (n-1) * (2*max_seq_length + 2)")
     con_sizes = np.where(multi, con_sizes, 0)

@@ -140,6 +140,16 @@ int fl_place_batch(fl_ctx *ctx, int set_id, const long long *con_begin, int flag
 int fl_fitness(fl_ctx *ctx, int pos_set, int neg_set, int method, double gamma, double *out);
 
 /*
+ * The same reduction, but the statistics stay on the device: *out_dev is a context-owned buffer of
+ * max(n_org, pad_rows) x 5 doubles (rows beyond n_org are zero), valid until the next fl_fitness* call.
+ * Asynchronous on fl_ctx_stream(); no device-to-host copy.  This is the send buffer of the one collective of the
+ * multi-GPU path: every rank all-gathers its equally padded block in place (NCCL), replacing the reference's
+ * comm.gather of pickled organisms and fitness lists (src/search_organisms.py:268-277).  Device errors (NaN null
+ * bin) surface at the next synchronising call (fl_sync).
+ */
+int fl_fitness_dev(fl_ctx *ctx, int pos_set, int neg_set, int method, double gamma, int pad_rows, void **out_dev);
+
+/*
  * One placement with the exact argument list of _multiplacement.calculate (src/_interface.c:45-185,
  * kwlist :49-52): sequence (+length), rec_types (+n_rec), rec_matrices, rec_lengths, con_matrices,
  * rec_scores (out, n+1), con_scores (out, n-1), con_lengths (out, n), max_length, bin_freqs, bin_edges,
@@ -156,6 +166,42 @@ int fl_calculate(fl_ctx *ctx, const char *sequence, int seq_len, const char *rec
  * kernel (too many near-ties, unknown bytes, tables outside its fixed-point range).  Synchronises.
  */
 int fl_path_stats(fl_ctx *ctx, long long *fast_pairs, long long *fallback_pairs);
+
+/*
+ * ---- table builders (host code, no device work, no context) -------------------------------------------------------
+ * The input producers of the path, batched and threaded; in the reference they are per-object Python loops.  They
+ * return the ARGUMENTS of the logarithms: the reference takes those with numpy's log2 / log, whose vector kernels are
+ * not bit-identical to libm's, so the Python layer applies numpy's function to the whole batch in one call.  Phi is
+ * evaluated with libm erf() (what math.erf calls) in the reference's operand order.
+ *
+ * fl_build_connector_tables replaces ConnectorObject.set_precomputed_pdfs_cdfs (connector_object.py:175-206) for n_con
+ * connectors of table length M:  pdf_arg[c*M + d] = Phi(d+.5) - Phi(d-.5) + pc,
+ * cdf_arg[c*M + d] = Phi(d-.5) - Phi(-.5) + pc*(d+1);  stored_pdfs / stored_cdfs = log2 of these.
+ * n_threads <= 0: all host cores.
+ */
+int fl_build_connector_tables(const double *mu, const double *sigma, int n_con, int M, double pseudo_count,
+                              double *pdf_arg, double *cdf_arg, int n_threads);
+/*
+ * In-place Python round(x, ndigits) (correctly rounded decimal, ties on the exact binary value): the rounding of
+ * PssmObject.recalculate_pssm (pssm_object.py:368-400), pssm = round(log2(4 p + pc), 2).
+ */
+int fl_round_decimals(double *values, long long n, int ndigits);
+/*
+ * Replaces the arithmetic of ShapeObject.set_alt_model (shape_object.py:156-180) for n_shapes recognizers whose bin
+ * edges are edges[edge_begin[s] .. +n_edges[s]):  auc_arg[s] = Phi(e_last) - Phi(e_0) + (n_edges-1)*pc and, packed one
+ * entry per bin (row s starts at edge_begin[s] - s),  mass_arg = Phi(e[b+1]) - Phi(e[b]) + pc;
+ * alt[b] = ln(mass_arg) - ln(auc_arg).  mu must already be clamped to [e_0, e_last] as the reference does first.
+ */
+int fl_build_shape_masses(const double *mu, const double *sigma, const double *edges, const long long *edge_begin,
+                          const int *n_edges, int n_shapes, double pseudo_count, double *mass_arg, double *auc_arg);
+
+/*
+ * Measures, on this device and now, the issue rate of the DPX instruction the DP stage consists of (VIADDMNMX:
+ * max(a + b, c), one per DP cell; as 32-bit and as packed 2 x 16-bit cells) in DP cells per second, and reports the
+ * SM count and the maximum SM clock.  bench.py divides its achieved cell rate by this (the ALU-bound roofline of
+ * SURVEY.md 8d); the reference has no counterpart (its DP is the scalar loop organism.c:347-371).
+ */
+int fl_measure_dpx_rate(fl_ctx *ctx, double *cells_per_s_i32, double *cells_per_s_i16x2, int *n_sm, int *sm_clock_khz);
 
 /* Counters for bench.py: kernels launched by this context since creation, and the last launch geometry. */
 long long fl_launch_count(fl_ctx *ctx);

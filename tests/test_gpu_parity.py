@@ -311,3 +311,137 @@ def test_adversarial_population_fast_path_equals_exact_path_and_oracle(engine):
         n = len(orgs[o].recognizer_types)
         assert mine.energies[o, s] == e and np.array_equal(mine.gaps[o, s, :n], gaps)
         assert np.array_equal(mine.rec_scores[o, s, :n], rs) and np.array_equal(mine.con_scores[o, s, :n - 1], cs)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the BASELINE configurations at FULL size: sampled pairs against the oracle, size-independent properties, and no
+# hand-backs on the workloads the bench reports
+# ---------------------------------------------------------------------------------------------------------------
+import functools
+
+
+@functools.lru_cache(maxsize=None)
+def _workload(name):
+    from flemingo_b200 import synthetic
+    return synthetic.make_workload(name)
+
+
+def _check_sampled_pairs(engine, orgs, seqs, energies, n_pairs, seed):
+    rng = np.random.default_rng(seed)
+    for o, s in zip(rng.integers(0, len(orgs), n_pairs), rng.integers(0, len(seqs), n_pairs)):
+        e = oracle.place(orgs[o], seqs[s])[0]
+        assert energies[o, s] == e, (o, s, energies[o, s], e)
+
+
+def _check_traced_slice(engine, orgs, seqs, pick_orgs, n_pairs, seed):
+    """Offsets and node scores of a slice of the population on the whole set; sampled pairs against the oracle."""
+    sub = [orgs[i] for i in pick_orgs]
+    engine.upload_population(sub)
+    res = engine.place(engine.upload_sequences(seqs, 0), trace=True)
+    rng = np.random.default_rng(seed)
+    for o, s in zip(rng.integers(0, len(sub), n_pairs), rng.integers(0, len(seqs), n_pairs)):
+        e, rs, cs, gaps, _ = oracle.place(sub[o], seqs[s])
+        n = len(sub[o].recognizer_types)
+        assert res.energies[o, s] == e and np.array_equal(res.gaps[o, s, :n], gaps)
+        assert np.array_equal(res.rec_scores[o, s, :n], rs) and np.array_equal(res.con_scores[o, s, :n - 1], cs)
+    # chain validity for every pair of the slice
+    lens = np.zeros((len(sub), res.gaps.shape[2]), dtype=np.int64)
+    for i, o in enumerate(sub):
+        lens[i, :len(o.recognizer_lengths)] = o.recognizer_lengths
+    end = res.gaps.astype(np.int64).sum(axis=2) + lens.sum(axis=1)[:, None]
+    assert (res.gaps >= 0).all() and (end <= len(seqs[0])).all()
+    return res
+
+
+def test_full_size_config3_vs_oracle(engine):
+    """BASELINE config 3 at full size: 2000 mixed organisms x 10 000 sequences of 300 bp (20 M placements)."""
+    orgs, pos, neg = _workload("c3")
+    seqs = pos + neg
+    engine.upload_population(orgs)
+    sset = engine.upload_sequences(seqs, 0)
+    engine.path_stats()
+    res = engine.place(sset)
+    fast, handed_back = engine.path_stats()
+    assert res.energies.shape == (2000, 10000)
+    if not engine.exact_only:
+        assert fast > 0.8 * res.energies.size          # organisms with >= 2 recognizers take the integer path ...
+        assert handed_back == 0                        # ... and none of their pairs is handed back on this workload
+    _check_sampled_pairs(engine, orgs, seqs, res.energies, 320, 1)
+    # sharded == unsharded, bit for bit: the same organisms in another batch composition give the same doubles
+    pick = np.arange(0, 2000, 37)
+    traced = _check_traced_slice(engine, orgs, seqs, pick, 120, 2)
+    assert np.array_equal(traced.energies, res.energies[pick])
+    # fitness statistics of the full batch against numpy on the device energies
+    sp, sn = engine.upload_sequences(pos, 0), engine.upload_sequences(neg, 1)
+    engine.upload_population(orgs)
+    engine.place(sp, fetch=False)
+    engine.place(sn, fetch=False)
+    stats = engine.fitness(sp, sn, "Welch", 0.2)
+    for o in range(0, 2000, 97):
+        want = oracle.fitness_stats(res.energies[o, :5000], res.energies[o, 5000:], "Welch", 0.2)
+        assert np.allclose(stats[o], want, rtol=FIT_RTOL)
+
+
+def test_full_size_config4_vs_oracle(engine):
+    """BASELINE config 4 at full size: 512 organisms x 5000 sequences of 2 kb, wide gap windows (P ~ 1965)."""
+    orgs, pos, neg = _workload("c4")
+    seqs = pos + neg
+    engine.upload_population(orgs)
+    sset = engine.upload_sequences(seqs, 0)
+    engine.path_stats()
+    res = engine.place(sset)
+    fast, handed_back = engine.path_stats()
+    assert res.energies.shape == (512, 5000)
+    if not engine.exact_only:
+        assert fast == res.energies.size and handed_back == 0
+    _check_sampled_pairs(engine, orgs, seqs, res.energies, 300, 3)
+    traced = _check_traced_slice(engine, orgs, seqs[:500], np.arange(0, 512, 16), 40, 4)
+    assert np.array_equal(traced.energies, res.energies[::16, :500])
+
+
+def test_full_size_config5_generation_vs_oracle(engine):
+    """BASELINE config 5, one generation's evaluation at full size: 4096 mixed organisms x 40 000 sequences."""
+    if engine.exact_only or "FLEMINGO_FAST_ROWS" in __import__("os").environ:
+        pytest.skip("full config 5 is checked once, in the default kernel mode")
+    orgs, pos, neg = _workload("c5")
+    engine.upload_population(orgs)
+    sp, sn = engine.upload_sequences(pos, 0), engine.upload_sequences(neg, 1)
+    engine.path_stats()
+    ep = engine.place(sp).energies
+    engine.place(sn, fetch=False)
+    fast, handed_back = engine.path_stats()
+    assert ep.shape == (4096, 20000) and handed_back == 0 and fast > 0.8 * 2 * ep.size
+    _check_sampled_pairs(engine, orgs, pos, ep, 300, 5)
+    stats = engine.fitness(sp, sn, "Welch", 0.2)
+    en = engine.place(sn).energies
+    for o in range(0, 4096, 211):
+        assert np.allclose(stats[o], oracle.fitness_stats(ep[o], en[o], "Welch", 0.2), rtol=FIT_RTOL)
+
+
+def test_minus_infinity_pssm_entries(engine):
+    """A -inf PSSM entry (not producible by recalculate_pssm, but legal input to calculate): where every chain through a
+    cell is -inf the reference's strict '<' never fires and its calloc'ed zeros stay in the outputs (organism.c:365)."""
+    from flemingo_b200 import synthetic
+    orgs = synthetic.pssm_organisms(3, 60, 21, n_rec=3, rec_len=4)
+    for org in orgs:
+        org.recognizers_flat = org.recognizers_flat.copy()
+        org.recognizers_flat[4 * 4 + 0] = -np.inf      # recognizer 1, column 0, base A
+        org.recognizers_flat[4 * 4 + 1] = -np.inf      # ... and G
+    seqs = ["a" * 60, "ag" * 30, "aaaagggg" * 7 + "aaaa"] + synthetic.random_sequences(4, 60, 22)
+    res = _assert_equals_oracle(engine, orgs, seqs)
+    if oracle.reference_module() is not None:      # pin the restatement on this unusual input to the reference itself
+        for o, org in enumerate(orgs):
+            for s, seq in enumerate(seqs):
+                e, rs, cs, gaps, _ = oracle.place(org, seq, "reference")
+                assert (res.energies[o, s] == e or (np.isnan(e) and np.isnan(res.energies[o, s])))
+                assert np.array_equal(res.gaps[o, s, :3], gaps) and np.array_equal(res.rec_scores[o, s, :3], rs, equal_nan=True)
+                assert np.array_equal(res.con_scores[o, s, :2], cs)
+
+
+def test_single_recognizer_on_a_long_sequence(engine):
+    """One recognizer, no connector: DEN_EXPANSION is never read, so sequences beyond 10 kb are placed."""
+    from flemingo_b200 import synthetic
+    rng = np.random.default_rng(23)
+    one = synthetic.assemble("one", [synthetic.random_pssm(rng, 9)], [])
+    seqs = synthetic.random_sequences(2, 10500, 24)
+    _assert_equals_oracle(engine, [one], seqs)

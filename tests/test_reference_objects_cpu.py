@@ -59,3 +59,36 @@ def test_packer_on_reference_objects_matches_mirror(golden, golden_cases):
     lengths = [L for L in lengths if L >= longest]
     assert np.array_equal(a.con_begin_for_lengths(lengths), b.con_begin_for_lengths(lengths))
     assert a.con_pool.tobytes() == b.con_pool.tobytes()
+
+
+def test_closed_form_rescale_equals_reference_adjust_scores():
+    """population.rescale_connector_block (closed form) writes the same doubles as the reference's
+    ConnectorObject.adjust_scores loop (connector_object.py:454-487) wherever get_placement can call it."""
+    sys.path.insert(0, str(REF / "src"))
+    try:
+        from objects.connector_object import ConnectorObject
+    finally:
+        sys.path.remove(str(REF / "src"))
+    conf = json.load(open(REF / "src" / "config.json"))["connector"]
+    from flemingo_b200.population import rescale_connector_block
+    rng = np.random.default_rng(11)
+    checked = 0
+    for _ in range(200):
+        M = int(rng.integers(20, 320))
+        S = int(rng.integers(10, M + 1))
+        sum_len = int(rng.integers(1, S + 1))
+        mu = float(S + 0.5 + rng.choice([1e-9, 0.5, 3.0, 40.0, 1e4]) * rng.uniform(1, 2))
+        sigma = float(rng.choice([1e-300, 1e-120, 1e-100, 1e-5, 0.3, 2.0, 50.0]))
+        con = ConnectorObject(conf, M, mu, sigma)
+        want = np.full(2 * M, -7.0)
+        got = want.copy()
+        try:
+            con.adjust_scores(want, S, sum_len)
+        except OverflowError:      # a denormal sigma overflows the reference's float power: same exception here
+            with pytest.raises(OverflowError):
+                rescale_connector_block(got, mu, sigma, con.pseudo_count, M, S, sum_len)
+            continue
+        rescale_connector_block(got, mu, sigma, con.pseudo_count, M, S, sum_len)
+        assert got.tobytes() == want.tobytes(), (M, S, sum_len, mu, sigma)
+        checked += 1
+    assert checked > 150
