@@ -321,10 +321,11 @@ class OrganismObject:
         self.fitness = stats[0]
 
 
-def build_placement(org_id, sequence, rec_types, rec_lengths, energy, rec_scores, con_scores, gaps) -> PlacementObject:
-    """Fills a PlacementObject from the kernel outputs exactly as organism_object.py:1337-1355 does."""
+def build_placement(org_id, sequence, rec_types, rec_lengths, energy, rec_scores, con_scores, gaps, placement_cls=None):
+    """Fills a PlacementObject from the kernel outputs exactly as organism_object.py:1337-1355 does.
+    placement_cls: the class to instantiate (the reference's own PlacementObject when its driver is running)."""
     n = len(rec_types)
-    placement = PlacementObject(org_id, sequence)
+    placement = (placement_cls or PlacementObject)(org_id, sequence)
     placement.set_energy(float(energy))
     placement.set_recognizer_scores([float(s) for s in rec_scores[:n]])
     placement.set_connectors_scores([float(s) for s in con_scores[:n - 1]])
