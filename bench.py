@@ -302,7 +302,7 @@ def measure_workload(args, name: str, scaling: str, rank: int, world: int, devic
     t_wall1 = time.time()
     wall_ms = (t_wall1 - t_wall0) * 1e3
     launches = eng.launch_count - launches0
-    fast_pairs, handed_back = eng.path_stats()
+    fast_pairs, handed_back, second_chance = eng.path_stats(detail=True)
     clocks = sampler.stop(t_wall0, t_wall1) if sampler is not None else None
 
     # sharded == unsharded: a seeded sample of organisms from every shard, recomputed on this rank alone, must
@@ -349,12 +349,12 @@ def measure_workload(args, name: str, scaling: str, rank: int, world: int, devic
     cells_mean, adds_mean = cells_per_placement(orgs, w["seq_len"]) if orgs else (0.0, 0.0)
     t = torch.tensor([dev_ms, place_ms, e2e_s, wall_ms, e2e_res_s], dtype=torch.float64, device=device)
     sums = torch.tensor([float(fast_pairs), float(handed_back), cells_mean * n_local * n_seq, adds_mean * n_local * n_seq,
-                         float(launches)], dtype=torch.float64, device=device)
+                         float(launches), float(second_chance)], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
     dev_ms, place_ms, e2e_s, wall_ms, e2e_res_s = (float(x) for x in t.cpu())
-    fast_all, fb_all, cells_all, adds_all, launches_all = (float(x) for x in sums.cpu())
+    fast_all, fb_all, cells_all, adds_all, launches_all, retry_all = (float(x) for x in sums.cpu())
 
     placements = n_total_org * n_seq
     ms_per_step = dev_ms / args.steps
@@ -362,10 +362,10 @@ def measure_workload(args, name: str, scaling: str, rank: int, world: int, devic
     # dominant kernel = the placement kernels (integer DPX filter pass + exact refinement): all launches of a step,
     # max over ranks; algorithmic cells of the whole job / that time = whole-job cell rate, per GPU = / world
     k_ms = place_ms / args.steps
-    cells_per_s_gpu = cells_all / args.steps / (k_ms * 1e-3) / world
+    cells_per_s_gpu = cells_all / (k_ms * 1e-3) / world
     dpx_peak = peak["cells_per_s_i32"]
     alu_peak = peak["n_sm"] * LANES_PER_SM * sm_max_mhz * 1e6 / 1e12
-    flop_eq = (3.0 * cells_all + adds_all) / args.steps / (k_ms * 1e-3) / world / 1e12
+    flop_eq = (3.0 * cells_all + adds_all) / (k_ms * 1e-3) / world / 1e12
     bytes_alg = placements * ((w["seq_len"] + 3) // 4 + 8) / world
     hbm_achieved = bytes_alg / (k_ms * 1e-3) / 1e9
     line = {"metric": METRIC, "value": placements / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -381,7 +381,8 @@ def measure_workload(args, name: str, scaling: str, rank: int, world: int, devic
                                   "note": "population uploaded every step; the two DNA sets stay resident in HBM"},
             "gpu_launches": int(launches_all),
             "hand_back_rate": (fb_all / fast_all) if fast_all else 0.0,
-            "hand_back": {"filter_pairs": int(fast_all), "handed_to_exact_kernel": int(fb_all)},
+            "hand_back": {"filter_pairs": int(fast_all), "handed_to_exact_kernel": int(fb_all),
+                          "int32_second_chance_after_packed_16bit_pass": int(retry_all)},
             "sharded_equals_unsharded": check,
             # primary line: the integer ALU pipe the DP runs on.  One cell = one VIADDMNMX = 2 integer ops (add, max);
             # the peak is the rate of that instruction MEASURED in this run on this device, x 2 ops

@@ -19,7 +19,7 @@ FIT_METHODS = {"Welch": 0, "Yuen": 1, "Trim-left-M": 2, "Trim-left-M-SD": 3}
 
 # every symbol include/flemingo_b200.h declares (tests check that the .so exports exactly these)
 EXPORTED = [
-    "fl_last_error", "fl_abi_version", "fl_ctx_create", "fl_ctx_destroy", "fl_ctx_stream", "fl_sync",
+    "fl_last_error", "fl_abi_version", "fl_device_count", "fl_ctx_create", "fl_ctx_destroy", "fl_ctx_stream", "fl_sync",
     "fl_upload_sequences", "fl_sequence_classes", "fl_upload_population", "fl_update_connectors", "fl_place_batch", "fl_fitness",
     "fl_fitness_dev",
     "fl_calculate", "fl_launch_count", "fl_path_stats", "fl_measure_dpx_rate",
@@ -62,6 +62,8 @@ def load_library() -> C.CDLL:
     lib.fl_last_error.restype = C.c_char_p
     lib.fl_last_error.argtypes = []
     lib.fl_abi_version.restype = ip
+    lib.fl_device_count.restype = ip
+    lib.fl_device_count.argtypes = []
     lib.fl_ctx_create.argtypes = [ip, vp, ll, C.POINTER(vp)]
     lib.fl_ctx_destroy.argtypes = [vp]
     lib.fl_ctx_stream.restype = vp
@@ -79,7 +81,7 @@ def load_library() -> C.CDLL:
     lib.fl_build_connector_tables.argtypes = [vp, vp, ip, ip, dp, vp, vp, ip]
     lib.fl_round_decimals.argtypes = [vp, ll, ip]
     lib.fl_build_shape_masses.argtypes = [vp, vp, vp, vp, vp, ip, dp, vp, vp]
-    lib.fl_path_stats.argtypes = [vp, C.POINTER(ll), C.POINTER(ll)]
+    lib.fl_path_stats.argtypes = [vp, C.POINTER(ll), C.POINTER(ll), C.POINTER(ll)]
     lib.fl_launch_count.restype = ll
     lib.fl_launch_count.argtypes = [vp]
     for name in EXPORTED:

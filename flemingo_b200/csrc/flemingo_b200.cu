@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -65,7 +66,7 @@ static const place_kernel_fn kPlaceKernels[kNumTileSizes][2] = {
     {place_tiled_kernel<5, false>, place_tiled_kernel<5, true>}, {place_tiled_kernel<7, false>, place_tiled_kernel<7, true>},
     {place_tiled_kernel<9, false>, place_tiled_kernel<9, true>}};
 
-typedef void (*list_kernel_fn)(const PlaceParams, const ListBuckets, const int *, const int *, unsigned long long *);
+typedef void (*list_kernel_fn)(const PlaceParams, const ListBuckets, const int *, const int *, const int *);
 static const list_kernel_fn kListKernels[kNumTileSizes][2] = {
     {place_list_kernel<1, false>, place_list_kernel<1, true>}, {place_list_kernel<3, false>, place_list_kernel<3, true>},
     {place_list_kernel<5, false>, place_list_kernel<5, true>}, {place_list_kernel<7, false>, place_list_kernel<7, true>},
@@ -78,42 +79,50 @@ static int pick_tile(int P) {
   return kNumTileSizes - 1;
 }
 
-// Integer fast path: (tile size J, lanes per pair TEAM).  A team covers 2*TEAM*J offsets per folded round.
+// Integer fast path: (tile size J, lanes per pair TEAM, arithmetic).  A team covers 2*TEAM*J offsets per folded round.
+// bits = 32: one DPX instruction per cell, fits every organism; bits = 16: packed rows, two cells per instruction, for
+// organisms whose whole value range fits int16 at a useful scale (place_fast_kernel.cuh); J = 2 * odd there (bank layout).
 typedef void (*fast_kernel_fn)(const FastParams);
 struct FastConfig {
-  int J, team;
+  int J, team, bits;
   fast_kernel_fn fn;
 };
-#define FAST_CFG(J, T) {J, T, place_fast_kernel<J, T>}
+#define FAST_CFG(J, T) {J, T, 32, place_fast_kernel<J, T, 32>}
+#define FAST_CFG16(J, T) {J, T, 16, place_fast_kernel<J, T, 16>}
 static const FastConfig kFastConfigs[] = {
     FAST_CFG(3, 8),  FAST_CFG(5, 8),  FAST_CFG(7, 8),  FAST_CFG(9, 8),  FAST_CFG(11, 8), FAST_CFG(13, 8), FAST_CFG(15, 8),
     FAST_CFG(17, 8), FAST_CFG(19, 8), FAST_CFG(21, 8), FAST_CFG(9, 16), FAST_CFG(11, 16), FAST_CFG(13, 16), FAST_CFG(15, 16), FAST_CFG(17, 16), FAST_CFG(19, 16),
-    FAST_CFG(21, 16), FAST_CFG(13, 32), FAST_CFG(17, 32), FAST_CFG(21, 32)};
+    FAST_CFG(21, 16), FAST_CFG(13, 32), FAST_CFG(17, 32), FAST_CFG(21, 32),
+    FAST_CFG16(6, 8), FAST_CFG16(10, 8), FAST_CFG16(14, 8), FAST_CFG16(18, 8), FAST_CFG16(22, 8), FAST_CFG16(10, 16), FAST_CFG16(14, 16),
+    FAST_CFG16(18, 16), FAST_CFG16(22, 16), FAST_CFG16(14, 32), FAST_CFG16(18, 32), FAST_CFG16(22, 32)};
 constexpr int kNumFastConfigs = (int)(sizeof(kFastConfigs) / sizeof(kFastConfigs[0]));
 
-// Estimated issue slots per pair: tiles x (J*J cells + loads and bookkeeping), scaled by the share of the warp a team uses.
-static double fast_cost(int P, int J, int team) {
+// Estimated issue slots per pair: tiles x (cells + loads and bookkeeping), scaled by the share of the warp a team uses.
+static double fast_cost(int P, int J, int team, int bits) {
   const int NB = (P + J - 1) / J;
+  const double full = bits == 16 ? J * J / 2.0 + 2.5 * J + 24.0 : J * J + 3.0 * J + 24.0;
+  const double diag = bits == 16 ? J * (J + 2) / 4.0 + 1.5 * J + 24.0 : J * (J + 1) / 2 + 2.0 * J + 24.0;
   double slots = 0;
   for (int r0 = 0; r0 < NB; r0 += 2 * team) {
     const int nbr = std::min(2 * team, NB - r0);
-    const int iters = 2 * r0 + nbr + 1;  // dp_stage: iters - 1 full tiles, then one diagonal tile of J(J+1)/2 cells
-    slots += (iters - 1) * (J * J + 3.0 * J + 24.0) + (J * (J + 1) / 2 + 2.0 * J + 24.0);
+    const int iters = 2 * r0 + nbr + 1;  // dp_stage: iters - 1 full tiles, then one diagonal tile
+    slots += (iters - 1) * full + diag;
   }
   return slots * team / 32.0;
 }
-static int pick_fast(int P) {
-  int best = 0;
+static int pick_fast(int P, int bits) {
+  int best = -1;
   double best_cost = 1e300;
-  // experiments: FLEMINGO_FAST_CFG="J,TEAM" forces one configuration
+  // experiments: FLEMINGO_FAST_CFG="J,TEAM" forces one configuration (of the arithmetic that has it)
   if (const char *force = getenv("FLEMINGO_FAST_CFG")) {
     int fj = 0, ft = 0;
     if (sscanf(force, "%d,%d", &fj, &ft) == 2)
       for (int i = 0; i < kNumFastConfigs; ++i)
-        if (kFastConfigs[i].J == fj && kFastConfigs[i].team == ft) return i;
+        if (kFastConfigs[i].J == fj && kFastConfigs[i].team == ft && kFastConfigs[i].bits == bits) return i;
   }
   for (int i = 0; i < kNumFastConfigs; ++i) {
-    const double c = fast_cost(P, kFastConfigs[i].J, kFastConfigs[i].team);
+    if (kFastConfigs[i].bits != bits) continue;
+    const double c = fast_cost(P, kFastConfigs[i].J, kFastConfigs[i].team, bits);
     if (c < best_cost) {
       best_cost = c;
       best = i;
@@ -170,7 +179,12 @@ struct Population {
   std::vector<int> rec_begin, sum_len, con_M, pool_len;
   int n_classes = 0, max_class_len = 0;
   unsigned long long class_signature = 0;
-  std::vector<int> kmer_need;  // ints of 4-mer tables if the organism is PSSM-only with >= 2 recognizers, else -1
+  std::vector<int> kmer_need;  // ints of the integer pass's tables if the organism has >= 2 recognizers, else -1
+  // upper bounds on the value ranges of the recognizer tables (energy units), for the host's choice between the 16-bit
+  // and the 32-bit integer pass
+  std::vector<double> rec_range;
+  std::vector<int> n_units;    // rounded tables per organism (4-mer groups + shape recognizers): error budget
+  std::vector<char> pssm_only; // every recognizer of the organism is a PSSM
   long long n_con = 0;
   int max_pool = 0, min_sum_len = 0;
   DevBuf d_rec_begin, d_rec_type, d_rec_len, d_rec_nb, d_rec_data, d_pool_begin, d_rec_pool, d_con_M, d_con_pool, d_sum_len, d_rec_class, d_cls_kind, d_cls_len, d_cls_nb, d_cls_edges, d_edges_pool;
@@ -179,8 +193,9 @@ struct Population {
 struct fl_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  DevBuf tables, err_flag, con_begin, org_list, gaps, rsc, csc, fit_out, fit_scratch, fb_item_count, fb_item_seqs, fast_scratch, fb_total, work_counters;
+  DevBuf tables, err_flag, con_begin, org_list, gaps, rsc, csc, fit_out, fit_scratch, fb_item_count, fb_item_seqs, fb_unit_begin, fast_scratch, fb_total, fb_retried, work_counters;
   int fast_reg_warps[64] = {0};
+  std::vector<double> h_den;  // host copy of DEN_EXPANSION (fits_int16)
   long long fast_pairs = 0, fallback_pairs = 0;  // statistics of the last fl_place_batch
   Population pop, scratch_pop;
   SeqSet sets[FL_MAX_SETS + 1];  // the extra slot serves fl_calculate
@@ -188,7 +203,16 @@ struct fl_ctx {
 };
 
 extern "C" const char *fl_last_error(void) { return g_last_error.c_str(); }
-extern "C" int fl_abi_version(void) { return 1; }
+extern "C" int fl_abi_version(void) { return 2; }
+
+extern "C" int fl_device_count(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return count;
+}
 
 extern "C" int fl_ctx_create(int device, const double *tables, long long n_tables, fl_ctx **out) {
   if (!out || !tables) return fail(FL_E_ARG, "fl_ctx_create: null argument");
@@ -199,6 +223,7 @@ extern "C" int fl_ctx_create(int device, const double *tables, long long n_table
   CK(cudaSetDevice(device));
   fl_ctx *ctx = new fl_ctx();
   ctx->device = device;
+  ctx->h_den.assign(tables + T_DEN, tables + T_DEN + 10000);
   cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     delete ctx;
@@ -207,6 +232,8 @@ extern "C" int fl_ctx_create(int device, const double *tables, long long n_table
   int rc = ctx->tables.ensure(sizeof(double) * FL_N_TABLE_DOUBLES);
   if (rc == FL_OK) rc = ctx->err_flag.ensure(sizeof(int));
   if (rc == FL_OK) rc = ctx->fb_total.ensure(sizeof(unsigned long long));
+  if (rc == FL_OK) rc = ctx->fb_retried.ensure(sizeof(unsigned long long));
+  if (rc == FL_OK && cudaMemsetAsync(ctx->fb_retried.p, 0, sizeof(unsigned long long), ctx->stream) != cudaSuccess) rc = fail(FL_E_CUDA, "memset failed");
   if (rc == FL_OK) rc = ctx->work_counters.ensure(1024 * sizeof(int));
   if (rc == FL_OK && cudaMemsetAsync(ctx->fb_total.p, 0, sizeof(unsigned long long), ctx->stream) != cudaSuccess) rc = fail(FL_E_CUDA, "memset failed");
   if (rc != FL_OK) {
@@ -252,7 +279,7 @@ extern "C" int fl_ctx_destroy(fl_ctx *ctx) {
   }
   release_pop(ctx->pop);
   release_pop(ctx->scratch_pop);
-  DevBuf *bufs[] = {&ctx->tables, &ctx->err_flag, &ctx->con_begin, &ctx->org_list, &ctx->gaps, &ctx->rsc, &ctx->csc, &ctx->fit_out, &ctx->fit_scratch, &ctx->fb_item_count, &ctx->fb_item_seqs, &ctx->fast_scratch, &ctx->fb_total, &ctx->work_counters};
+  DevBuf *bufs[] = {&ctx->tables, &ctx->err_flag, &ctx->con_begin, &ctx->org_list, &ctx->gaps, &ctx->rsc, &ctx->csc, &ctx->fit_out, &ctx->fit_scratch, &ctx->fb_item_count, &ctx->fb_item_seqs, &ctx->fb_unit_begin, &ctx->fast_scratch, &ctx->fb_total, &ctx->fb_retried, &ctx->work_counters};
   for (DevBuf *b : bufs) b->release();
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -385,6 +412,9 @@ static int upload_population(fl_ctx *ctx, Population &P, const fl_population *po
   P.con_M.assign(pop->con_M, pop->con_M + n_org);
   P.pool_len.assign(n_org, 0);
   P.kmer_need.assign(n_org, -1);
+  P.rec_range.assign((size_t)pop->n_rec_total, 0.0);
+  P.n_units.assign(n_org, 0);
+  P.pssm_only.assign(n_org, 1);
   P.max_rec = 0;
   P.max_pool = 0;
   P.min_sum_len = 0x7fffffff;
@@ -411,12 +441,41 @@ static int upload_population(fl_ctx *ctx, Population &P, const fl_population *po
     P.pool_len[o] = (int)(pop->pool_begin[o + 1] - pop->pool_begin[o]);
     {
       // ints the integer fast path needs for this organism: 4-mer tables per PSSM, one bin table per shape recognizer
-      int need = 0;
+      int need = 0, units = 0;
       for (int i = 0; i < n; ++i) {
         const char t = pop->rec_type[rb + i];
-        need += (t == 'p' || t == 'P') ? 256 * ((pop->rec_len[rb + i] + 3) / 4) : pop->rec_nb[rb + i] - 1;
+        const bool is_p = (t == 'p' || t == 'P');
+        const int L = pop->rec_len[rb + i];
+        need += is_p ? 256 * ((L + 3) / 4) : pop->rec_nb[rb + i] - 1;
+        units += is_p ? (L + 3) / 4 : 1;
+        if (!is_p) P.pssm_only[o] = 0;
+        if (n >= 2) {
+          // value range of the recognizer's scores (what build_fast_plan computes on the device)
+          const double *m = pop->rec_pool + pop->rec_data[rb + i];
+          double range = 0.0;
+          if (is_p) {
+            for (int c = 0; c < L; ++c) {
+              const double lo = std::min(std::min(m[4 * c], m[4 * c + 1]), std::min(m[4 * c + 2], m[4 * c + 3]));
+              const double hi = std::max(std::max(m[4 * c], m[4 * c + 1]), std::max(m[4 * c + 2], m[4 * c + 3]));
+              range += hi - lo;
+            }
+          } else {
+            const int nbins = pop->rec_nb[rb + i] - 1;
+            double lo = INFINITY, hi = -INFINITY;
+            for (int b = 0; b < nbins; ++b) {
+              double x = m[nbins + b] - m[b];
+              if (x != x) continue;
+              if (x < -1e10) x = -1e10;
+              lo = std::min(lo, x);
+              hi = std::max(hi, x);
+            }
+            range = hi - lo;
+          }
+          P.rec_range[rb + i] = (range == range) ? range : INFINITY;
+        }
       }
       P.kmer_need[o] = n >= 2 ? need : -1;
+      P.n_units[o] = units;
     }
     P.max_rec = std::max(P.max_rec, n);
     P.max_pool = std::max(P.max_pool, P.pool_len[o]);
@@ -514,6 +573,46 @@ extern "C" int fl_update_connectors(fl_ctx *ctx, const double *con_pool, long lo
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->pop.n_con = n_con;
   return FL_OK;
+}
+
+// Which organisms take the packed 16-bit integer pass.  PSSM-only organisms whose value range fits: their scores are
+// diverse (a 2-decimal PSSM entry per column), so even at 32-128 units per energy unit a stage keeps one or two
+// candidate cells.  Organisms with shape recognizers stay on the int32 pass: a shape score takes one of 25 bin values
+// and neighbouring offsets share bins, so near-ties are the rule, the 16-bit thresholds let 2-18 % of their pairs
+// overflow the candidate lists (measured on config 3 per organism class), and their refinement costs more than the DP
+// saves (config 3: 32 ms per launch on the packed pass against ~16 ms on int32 for the same items).
+// Host-side estimate of build_fast_plan<16>'s scale for organism o on sequences of length S, from UPPER bounds of the
+// table ranges: recognizers from the uploaded tables, a connector's gap energies from  pdf in [log2(1e-15), 0]  plus
+// the spread of the combinatorial term den(g) (connector.c:51-56).  True when the packed 16-bit integer pass will
+// accept the organism at a scale of at least 32 units per energy unit (the device re-derives the plan from the real
+// ranges and hands the organism's pairs to the exact kernel should it disagree).
+static bool fits_int16(fl_ctx *ctx, const Population &P, int o, int S, std::map<long long, double> &den_cache) {
+  if (const char *force = getenv("FLEMINGO_FAST_BITS")) return atoi(force) == 16;
+  const int rb = P.rec_begin[o], n = P.rec_begin[o + 1] - rb;
+  if (n < 2 || !P.pssm_only[o]) return false;
+  const int Pn = S - P.sum_len[o] + 1, eff = S - P.sum_len[o] + n;
+  if (Pn < 2 || eff > 10000) return false;
+  const long long key = ((long long)n << 32) | (unsigned)P.sum_len[o];
+  auto it = den_cache.find(key);
+  if (it == den_cache.end()) {
+    const double *D = ctx->h_den.data();
+    double lo = INFINITY, hi = -INFINITY;
+    for (int g = 0; g <= Pn - 2; ++g) {
+      const double den = (D[(eff - (g + 1)) - 1] - D[(n - 1) - 1] - D[eff - (g + 1) - (n - 1) - 1]) - (D[eff - 1] - D[n - 1] - D[eff - n - 1]);
+      lo = std::min(lo, den);
+      hi = std::max(hi, den);
+    }
+    it = den_cache.emplace(key, hi - lo).first;
+  }
+  const double gr = 50.0 + it->second;
+  double cum = P.rec_range[rb], need = 0.0;
+  for (int c = 0; c < n - 1; ++c) {
+    need = std::max(need, 2.0 * cum + gr);
+    cum += gr + P.rec_range[rb + c + 1];
+  }
+  need = std::max(need, cum);
+  const double budget = (double)kBudget16 - 4.0 * (P.n_units[o] + n) - 16.0;
+  return need == need && need > 0.0 && budget / need >= 32.0;
 }
 
 static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long *con_begin, int flags, double *energies,
@@ -657,12 +756,13 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
     fp.want_trace = trace ? 1 : 0;
     fp.has_unk = set.has_unk.as<unsigned char>();
     int kmer_cap = 0;
+    std::map<long long, double> den_cache;
     std::vector<int> exact_bucket[kNumTileSizes], fast_bucket[kNumFastConfigs];
     long long n_fast_org = 0;
     for (int o = 0; o < n_org; ++o) {
       const int Po = cl.len - P.sum_len[o] + 1;
       if (allow_fast && P.kmer_need[o] > 0 && P.kmer_need[o] <= 16384 && Po >= 2) {
-        fast_bucket[pick_fast(Po)].push_back(o);
+        fast_bucket[pick_fast(Po, fits_int16(ctx, P, o, cl.len, den_cache) ? 16 : 32)].push_back(o);
         kmer_cap = std::max(kmer_cap, P.kmer_need[o]);
         ++n_fast_org;
       } else {
@@ -673,14 +773,20 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
     // fast-path geometry: warps per CTA chosen for the most resident warps per SM; if even one warp does not fit,
     // those organisms go to the exact kernel
     int fast_warps[kNumFastConfigs], fast_rowq[kNumFastConfigs], fast_slot[kNumFastConfigs], fast_ctas_per_sm[kNumFastConfigs];
-    bool fast_single[kNumFastConfigs] = {false};
+    bool fast_single[kNumFastConfigs] = {false}, fast_planned[kNumFastConfigs] = {false};
     size_t fast_smem[kNumFastConfigs];
     for (int j = 0; j < kNumFastConfigs; ++j) {
       fast_warps[j] = 0;
       fast_smem[j] = 0;
-      if (fast_bucket[j].empty()) continue;
+    }
+    // launch geometry of configuration j for this class (once); false if not even one warp fits
+    auto plan_config = [&](int j) -> bool {
+      if (fast_planned[j]) return fast_warps[j] > 0;
+      fast_planned[j] = true;
       const int team = kFastConfigs[j].team, nt = 32 / team;
-      fast_rowq[j] = (Pmax + kFastConfigs[j].J + 3) & ~3;
+      const int elem = kFastConfigs[j].bits / 8;                  // bytes per row element
+      const int align = 16 / elem;                                // row elements per 16 bytes (cp.async / vector stores)
+      fast_rowq[j] = (Pmax + kFastConfigs[j].J + align - 1) & ~(align - 1);
       int best_occ = 0;
       // multiples of four only: the DP stages are bound by the ALU pipe of each of the SM's four schedulers, so a
       // scheduler that holds one warp more than the others sets the pace (13 warps: 194 ms on config 3, 12 warps: 169 ms)
@@ -691,17 +797,23 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
       const char *force_rows = getenv("FLEMINGO_FAST_ROWS");
       for (int rows = 2; rows >= 1; --rows) {
         if (force_rows && atoi(force_rows) != rows) continue;
-        const int slot = ((rows * fast_rowq[j] + 31) & ~31) + (team & 31);
+        // slot stride in 32-bit words = TEAM (mod 32), so that the teams of a warp work on disjoint banks
+        const int slot_words = ((rows * fast_rowq[j] * elem / 4 + 31) & ~31) + (team & 31);
+        const int slot = slot_words * 4 / elem;                   // in row elements
         for (int nw : kWarpChoices) {
           if (force_w && atoi(force_w) != nw) continue;
-          const size_t d = (size_t)pp.pool_stride + (size_t)(P.max_rec - 1) * pp.g_stride + 2ull * nw * P.max_rec * kCandCap;
-          const size_t i = (size_t)(P.max_rec - 1) * fp.gq_stride + fp.kmer_cap + (size_t)nw * nt * slot +
-                           2ull * nw * P.max_rec * kCandCap + (size_t)nw * nt * P.max_rec;
+          const int cand_w = cand_per_warp(kFastConfigs[j].bits, nt);
+          const size_t d = (size_t)pp.pool_stride + (size_t)(P.max_rec - 1) * pp.g_stride + 2ull * nw * P.max_rec * cand_w;
+          const size_t i = (size_t)(P.max_rec - 1) * fp.gq_stride + fp.kmer_cap + (size_t)nw * nt * slot_words +
+                           2ull * nw * P.max_rec * cand_w + (size_t)nw * nt * P.max_rec;
           const size_t bytes = d * 8 + i * 4 + sizeof(RecDesc) * P.max_rec + sizeof(FastPlan) + 48 + (size_t)nw * nt * fp.k8_stride;
           if (bytes > (size_t)kMaxSmem) continue;
           const int ctas = (int)std::min<size_t>(233472 / (bytes + 1024), 32);
           const int reg_warps = ctx->fast_reg_warps[j];  // 16-19 for the 101-124 registers ptxas settles at
-          const int occ = nw * std::min(ctas, reg_warps / nw);  // whole CTAs only
+          // whole CTAs only; one large CTA beats several small ones at equal occupancy (the plan and the prologue are
+          // paid per CTA and the hardware scheduler favours one CTA's warps), and more than 16 resident warps bought
+          // with small CTAs measured slower (packed kernel on config 2: 5 CTAs of 4 warps 1.82 ms per launch, 1 CTA of 16 warps 1.39 ms)
+          const int occ = std::min(16, nw * std::min(ctas, reg_warps / nw)) * 64 + nw;
           if (occ > best_occ) {
             best_occ = occ;
             fast_warps[j] = nw;
@@ -712,7 +824,11 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
           }
         }
       }
-      if (!fast_warps[j]) {
+      return fast_warps[j] > 0;
+    };
+    for (int j = 0; j < kNumFastConfigs; ++j) {
+      if (fast_bucket[j].empty()) continue;
+      if (!plan_config(j)) {
         for (int o : fast_bucket[j]) exact_bucket[pick_tile(cl.len - P.sum_len[o] + 1)].push_back(o);
         n_fast_org -= (long long)fast_bucket[j].size();
         fast_bucket[j].clear();
@@ -751,24 +867,24 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
     }
     if (n_fast_org > 0) {
       ctx->fast_pairs += n_fast_org * cl.count;
-      // geometry of every bucket first, so that the hand-back lists can be sized before anything is launched
+      // Geometry of every launch first, so that the hand-back lists can be sized before anything is launched.
+      // A bucket of the packed 16-bit pass gets a SECOND-CHANCE launch of the int32 pass over the pairs it hands back
+      // (near-ties beyond its candidate lists are exact ties only at the int32 scale); what that launch hands back, and
+      // what the int32 buckets hand back, goes to the exact kernel.  Hand-back lists, in this order:
+      //   [16-bit buckets with a second chance] [16-bit buckets without] [int32 buckets] [second-chance launches]
+      // -- the exact list kernel reads everything from the second group on.
       struct Geo {
-        int j, spc, chunks, per_round, n_b;
-        long long items, grid;
+        int j, spc, chunks, per_round, n_b, org_begin, retry_of;
+        long long items, grid, item_base, pair_base;
       };
       std::vector<Geo> geo;
-      ListBuckets lb;
-      lb.n = 0;
-      lb.item_begin[0] = 0;
-      long long pair_slots = 0, scratch_ints = 0;
-      for (int j = 0; j < kNumFastConfigs; ++j) {
-        const int n_b = (int)fast_bucket[j].size();
-        if (!n_b) continue;
-        if (lb.n >= kMaxListBuckets) return fail(FL_E_UNSUPPORTED, "too many tile buckets");
+      auto make_geo = [&](int j, int n_b, int org_begin) {
         const int team = kFastConfigs[j].team, nt = 32 / team, nw = fast_warps[j];
         Geo g;
         g.j = j;
         g.n_b = n_b;
+        g.org_begin = org_begin;
+        g.retry_of = -1;
         g.per_round = nw * nt;
         const long long pairs = (long long)n_b * cl.count;
         const long long fast_target = (long long)n_sm * fast_ctas_per_sm[j] * 6;
@@ -779,18 +895,58 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
         g.chunks = (cl.count + spc - 1) / spc;
         g.items = (long long)n_b * g.chunks;
         g.grid = std::min<long long>(g.items, (long long)n_sm * fast_ctas_per_sm[j]);
-        if (lb.item_begin[lb.n] + g.items > 0x7fffffffLL) return fail(FL_E_UNSUPPORTED, "too many work items");
+        return g;
+      };
+      const bool allow_retry = !getenv("FLEMINGO_NO_RETRY");
+      std::vector<Geo> first16r, first16, first32, retries;
+      for (int j = 0; j < kNumFastConfigs; ++j) {
+        const int n_b = (int)fast_bucket[j].size();
+        if (!n_b) continue;
+        Geo g = make_geo(j, n_b, fast_begin[j]);
+        if (kFastConfigs[j].bits == 16) {
+          const int j32 = pick_fast(cl.len - P.sum_len[fast_bucket[j][0]] + 1, 32);
+          if (allow_retry && j32 >= 0 && plan_config(j32)) {
+            Geo r = g;   // same items, same per-item lists; another kernel
+            r.j = j32;
+            r.per_round = fast_warps[j32] * (32 / kFastConfigs[j32].team);
+            r.grid = std::min<long long>(r.items, (long long)n_sm * fast_ctas_per_sm[j32]);
+            r.retry_of = (int)first16r.size();
+            first16r.push_back(g);
+            retries.push_back(r);
+          } else {
+            first16.push_back(g);
+          }
+        } else {
+          first32.push_back(g);
+        }
+      }
+      const int n_first16r = (int)first16r.size();
+      for (const std::vector<Geo> *grp : {&first16r, &first16, &first32, &retries}) geo.insert(geo.end(), grp->begin(), grp->end());
+      if ((int)geo.size() - n_first16r > kMaxListBuckets) return fail(FL_E_UNSUPPORTED, "too many tile buckets");
+      long long total_items = 0, pair_slots = 0, scratch_ints = 0;
+      for (Geo &g : geo) {
+        g.item_base = total_items;
+        g.pair_base = pair_slots;
+        total_items += g.items;
+        pair_slots += g.items * g.spc;
+        scratch_ints = std::max(scratch_ints, g.grid * g.per_round * (long long)P.max_rec * fast_rowq[g.j]);  // upper bound for both element sizes
+        if (total_items > 0x7fffffffLL) return fail(FL_E_UNSUPPORTED, "too many work items");
+      }
+      // what the exact list kernel reads: every launch from the second group on
+      ListBuckets lb;
+      lb.n = 0;
+      lb.item_begin[0] = 0;
+      const long long list_item_base = n_first16r ? geo[n_first16r].item_base : 0;
+      for (size_t b = n_first16r; b < geo.size(); ++b) {
+        const Geo &g = geo[b];
         lb.chunks[lb.n] = g.chunks;
-        lb.spc[lb.n] = spc;
-        lb.org_begin[lb.n] = fast_begin[j];
-        lb.pair_base[lb.n] = pair_slots;
+        lb.spc[lb.n] = g.spc;
+        lb.org_begin[lb.n] = g.org_begin;
+        lb.pair_base[lb.n] = g.pair_base;
         lb.item_begin[lb.n + 1] = lb.item_begin[lb.n] + (int)g.items;
         ++lb.n;
-        pair_slots += g.items * spc;
-        scratch_ints = std::max(scratch_ints, g.grid * g.per_round * (long long)P.max_rec * fast_rowq[j]);
-        geo.push_back(g);
       }
-      const int total_items = lb.item_begin[lb.n];
+      const int list_items = lb.item_begin[lb.n];
       if ((rc = ctx->fb_item_count.ensure((size_t)total_items * 4 + 4)) || (rc = ctx->fb_item_seqs.ensure((size_t)pair_slots * 4 + 4)) ||
           (rc = ctx->fast_scratch.ensure((size_t)scratch_ints * 4)))
         return rc;
@@ -798,25 +954,34 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
       fp.fb_item_count = ctx->fb_item_count.as<int>();
       fp.fb_item_seqs = ctx->fb_item_seqs.as<int>();
       fp.scratch = ctx->fast_scratch.as<int>();
+      fp.retried_total = ctx->fb_retried.as<unsigned long long>();
       for (size_t b = 0; b < geo.size(); ++b) {
         const Geo &g = geo[b];
         const int j = g.j, nw = fast_warps[j];
         fp.rowq_stride = fast_rowq[j];
+        fp.cand_w = cand_per_warp(kFastConfigs[j].bits, 32 / kFastConfigs[j].team);
         fp.slotq_stride = fast_slot[j];
         fp.single_row = fast_single[j] ? 1 : 0;
         fp.scratch_slot_stride = (long long)P.max_rec * fast_rowq[j];
         fp.base = pp;
-        fp.base.org_list = d_list + fast_begin[j];
+        fp.base.org_list = d_list + g.org_begin;
         fp.base.seqs_per_cta = g.spc;
         fp.base.chunks = g.chunks;
         fp.n_items = (int)g.items;
-        fp.item_base = lb.item_begin[b];
-        fp.pair_base = lb.pair_base[b];
+        fp.item_base = (int)g.item_base;
+        fp.pair_base = g.pair_base;
+        fp.retry_count = nullptr;
+        fp.retry_seqs = nullptr;
+        if (g.retry_of >= 0) {  // second chance: the item's sequences are the ones its first launch handed back
+          fp.retry_count = fp.fb_item_count + geo[g.retry_of].item_base;
+          fp.retry_seqs = fp.fb_item_seqs + geo[g.retry_of].pair_base;
+        }
         fp.work_counter = ctx->work_counters.as<int>() + (ctx->launches % 1024);
         CK(cudaMemsetAsync(fp.work_counter, 0, sizeof(int), ctx->stream));
         if (getenv("FLEMINGO_DEBUG_LAUNCH"))
-          fprintf(stderr, "fast launch: cfg J=%d team=%d warps=%d ctas/sm=%d grid=%lld items=%lld spc=%d smem=%zu rows=%d\n", kFastConfigs[j].J,
-                  kFastConfigs[j].team, nw, fast_ctas_per_sm[j], g.grid, g.items, g.spc, fast_smem[j], fast_single[j] ? 1 : 2);
+          fprintf(stderr, "fast launch%s: cfg bits=%d J=%d team=%d warps=%d ctas/sm=%d grid=%lld items=%lld spc=%d smem=%zu rows=%d\n",
+                  g.retry_of >= 0 ? " (second chance)" : "", kFastConfigs[j].bits, kFastConfigs[j].J, kFastConfigs[j].team, nw,
+                  fast_ctas_per_sm[j], g.grid, g.items, g.spc, fast_smem[j], fast_single[j] ? 1 : 2);
         kFastConfigs[j].fn<<<(unsigned)g.grid, nw * 32, fast_smem[j], ctx->stream>>>(fp);
         CK(cudaGetLastError());
         ctx->launches++;
@@ -833,11 +998,17 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
         if (lsmem <= (size_t)kMaxSmem / 2 || lw == 1) break;
       }
       if (lsmem > (size_t)kMaxSmem) return fail(FL_E_UNSUPPORTED, "list-mode placement needs %zu bytes of shared memory (limit %d)", lsmem, kMaxSmem);
-      const unsigned lgrid = (unsigned)std::min<long long>(((long long)total_items + 31) / 32, (long long)n_sm * 4);
-      kListKernels[pick_tile(Pmax)][trace ? 1 : 0]<<<lgrid, lw * 32, lsmem, ctx->stream>>>(lp, lb, fp.fb_item_count, fp.fb_item_seqs,
-                                                                                          ctx->fb_total.as<unsigned long long>());
+      if ((rc = ctx->fb_unit_begin.ensure(((size_t)list_items + 1) * 4))) return rc;
+      const int *list_count = fp.fb_item_count + list_item_base;
+      list_units_kernel<<<1, 1024, 0, ctx->stream>>>(list_count, list_items, ctx->fb_unit_begin.as<int>(),
+                                                     ctx->fb_total.as<unsigned long long>());
       CK(cudaGetLastError());
-      ctx->launches++;
+      const int list_ctas_per_sm = std::max(1, std::min(4, (int)(233472 / (lsmem + 1024))));
+      const unsigned lgrid = (unsigned)((long long)n_sm * list_ctas_per_sm);
+      kListKernels[pick_tile(Pmax)][trace ? 1 : 0]<<<lgrid, lw * 32, lsmem, ctx->stream>>>(lp, lb, list_count, fp.fb_item_seqs,
+                                                                                          ctx->fb_unit_begin.as<int>());
+      CK(cudaGetLastError());
+      ctx->launches += 2;
     }
   }
   set.E_n_org = n_org;
@@ -861,11 +1032,12 @@ extern "C" int fl_place_batch(fl_ctx *ctx, int set_id, const long long *con_begi
   return place_batch(ctx, ctx->pop, ctx->sets[set_id], con_begin, flags, energies, gaps, rec_scores, con_scores);
 }
 
-extern "C" int fl_path_stats(fl_ctx *ctx, long long *fast_pairs, long long *fallback_pairs) {
+extern "C" int fl_path_stats(fl_ctx *ctx, long long *fast_pairs, long long *fallback_pairs, long long *second_chance_pairs) {
   if (!ctx) return fail(FL_E_ARG, "fl_path_stats: null context");
   CK(cudaSetDevice(ctx->device));
-  unsigned long long fb = 0;
+  unsigned long long fb = 0, retried = 0;
   CK(cudaMemcpyAsync(&fb, ctx->fb_total.p, sizeof fb, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(&retried, ctx->fb_retried.p, sizeof retried, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
 #ifdef FL_PHASE_CLOCKS
   {
@@ -899,8 +1071,10 @@ extern "C" int fl_path_stats(fl_ctx *ctx, long long *fast_pairs, long long *fall
 #endif
   if (fast_pairs) *fast_pairs = ctx->fast_pairs;
   if (fallback_pairs) *fallback_pairs = (long long)fb;
+  if (second_chance_pairs) *second_chance_pairs = (long long)retried;
   ctx->fast_pairs = 0;
   CK(cudaMemsetAsync(ctx->fb_total.p, 0, sizeof fb, ctx->stream));
+  CK(cudaMemsetAsync(ctx->fb_retried.p, 0, sizeof retried, ctx->stream));
   return FL_OK;
 }
 

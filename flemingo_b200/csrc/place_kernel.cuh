@@ -307,6 +307,143 @@ __device__ __forceinline__ void dp_stage(const typename Op::T *prev, typename Op
 }
 
 // ------------------------------------------------------------------------------------------------
+// Packed 16-bit variant of the stage: TWO cells per DPX instruction (VIADDMNMX.16x2).
+//   rows   int16, one entry per offset; a 32-bit load fetches (prev[k], prev[k+1]) for even k
+//   H      one 32-bit word per gap d:  lo half = G[d], hi half = G[d-1]  (any d, so no parity cases), holding the
+//          stage's sentinel for d outside [0, P-2] -- H[0] = (G[0], sentinel) masks the k = j+1 half of a diagonal pair
+//   acc[t] = (max over even k, max over odd k) of row t; the two halves are merged when the row block is flushed
+// A J x J tile (J even) is J * J/2 instructions plus J loads of H and J/2 loads of prev.  Lane stride of H is J words:
+// J = 2 * odd keeps the lanes of a team on distinct banks.  Same folding, same step order (so the same in-place
+// guarantee) as dp_stage.  The caller keeps every row value and every prev + H sum inside int16 (FastPlan16).
+// ------------------------------------------------------------------------------------------------
+constexpr unsigned kLowest16x2 = 0x80008000u;
+
+template <int J>
+__device__ __forceinline__ void flush16(const unsigned (&acc)[J], short *cur, int b) {
+  unsigned *dst = reinterpret_cast<unsigned *>(cur + b * J);  // J even and rows 4-byte aligned
+#pragma unroll
+  for (int t = 0; t < J; t += 2) {
+    const unsigned lo = __byte_perm(acc[t], acc[t + 1], 0x5410);  // (even-k max of row t, even-k max of row t+1)
+    const unsigned hi = __byte_perm(acc[t], acc[t + 1], 0x7632);  // (odd-k max of row t,  odd-k max of row t+1)
+    dst[t >> 1] = __vmaxs2(lo, hi);
+  }
+}
+
+template <int J>
+__device__ __forceinline__ void tile_switch16(unsigned (&A)[J], unsigned (&acc)[J], TileState &st, short *cur,
+                                              const unsigned *__restrict__ H) {
+  if (st.kb == st.kend) {
+    flush16<J>(acc, cur, st.b);
+    if (st.next_b >= 0) {
+      st.b = st.next_b;
+      st.next_b = -1;
+      st.kend = st.b + 1;
+    } else {
+      st.b = 0;
+      st.kend = -1;
+      st.kstep = 0;
+    }
+    st.kb = 0;
+    const unsigned *ha = H + st.b * J + (J - 1);
+#pragma unroll
+    for (int t = 0; t < J; ++t) {
+      acc[t] = kLowest16x2;
+      A[t] = ha[-t];
+    }
+  }
+}
+
+// A[i] = H[m + J-1 - i], B[i] = H[m - 1 - i] with m = (b - kb) * J: row t and the k pair u need H[m + t - 2u].
+template <int J>
+__device__ __forceinline__ void tile_step16(unsigned (&A)[J], unsigned (&B)[J], unsigned (&acc)[J], TileState &st,
+                                            const short *prev, short *cur, const unsigned *__restrict__ H) {
+  __syncwarp();
+  tile_switch16<J>(A, acc, st, cur, H);
+  const unsigned *hb = H + (st.b - st.kb) * J - 1;
+  const unsigned *pk = reinterpret_cast<const unsigned *>(prev + st.kb * J);
+  unsigned pv[J / 2];
+#pragma unroll
+  for (int u = 0; u < J; ++u) B[u] = hb[-u];
+#pragma unroll
+  for (int u = 0; u < J / 2; ++u) pv[u] = pk[u];
+#pragma unroll
+  for (int u = 0; u < J / 2; ++u) {
+#pragma unroll
+    for (int t = 0; t < J; ++t) {
+      const unsigned h = (t >= 2 * u) ? A[J - 1 - t + 2 * u] : B[2 * u - t - 1];
+      acc[t] = __viaddmax_s16x2(pv[u], h, acc[t]);
+    }
+  }
+  st.kb += st.kstep;
+}
+
+// the diagonal tile (kb == b, m = 0): only the pairs with k <= j; H[0]'s hi half masks k = j + 1
+template <int J>
+__device__ __forceinline__ void tile_last16(unsigned (&A)[J], unsigned (&acc)[J], TileState &st, const short *prev,
+                                            short *cur, const unsigned *__restrict__ H) {
+  __syncwarp();
+  tile_switch16<J>(A, acc, st, cur, H);
+  const unsigned *pk = reinterpret_cast<const unsigned *>(prev + st.kb * J);
+  unsigned pv[J / 2];
+#pragma unroll
+  for (int u = 0; u < J / 2; ++u) pv[u] = pk[u];
+#pragma unroll
+  for (int u = 0; u < J / 2; ++u) {
+#pragma unroll
+    for (int t = 2 * u; t < J; ++t) acc[t] = __viaddmax_s16x2(pv[u], A[J - 1 - t + 2 * u], acc[t]);
+  }
+  st.kb += st.kstep;
+}
+
+template <int J, int TEAM>
+__device__ __forceinline__ void dp_stage16(const short *prev, short *cur, const unsigned *__restrict__ H, int P, int tl) {
+  static_assert(J % 2 == 0, "packed stage needs an even tile size");
+  const int NB = (P + J - 1) / J;
+  for (int r0 = ((NB - 1) / (2 * TEAM)) * (2 * TEAM); r0 >= 0; r0 -= 2 * TEAM) {
+    const int nbr = min(2 * TEAM, NB - r0);
+    const int half = (nbr + 1) >> 1;
+    const int bA = r0 + tl, bB = r0 + nbr - 1 - tl;
+    TileState st;
+    if (tl < half) {
+      st.b = bB;
+      st.kend = bB + 1;
+      st.kstep = 1;
+      st.next_b = (bB > bA) ? bA : -1;
+    } else {
+      st.b = 0;
+      st.kend = -1;
+      st.kstep = 0;
+      st.next_b = -1;
+    }
+    st.kb = 0;
+    unsigned acc[J], A[J], B[J];
+    {
+      const unsigned *ha = H + st.b * J + (J - 1);
+#pragma unroll
+      for (int t = 0; t < J; ++t) {
+        acc[t] = kLowest16x2;
+        A[t] = ha[-t];
+      }
+    }
+    const int iters = 2 * r0 + nbr + 1;
+    int it = 0;
+    for (; it + 2 < iters; it += 2) {
+      tile_step16<J>(A, B, acc, st, prev, cur, H);
+      tile_step16<J>(B, A, acc, st, prev, cur, H);
+    }
+    if (iters - it == 2) {
+      tile_step16<J>(A, B, acc, st, prev, cur, H);
+    } else {
+#pragma unroll
+      for (int t = 0; t < J; ++t) B[t] = A[t];
+    }
+    tile_last16<J>(B, acc, st, prev, cur, H);
+    __syncwarp();
+    if (st.kstep) flush16<J>(acc, cur, st.b);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Shared pieces of the placement kernels
 // ------------------------------------------------------------------------------------------------
 struct OrgView {
@@ -502,11 +639,14 @@ __global__ void __launch_bounds__(256) place_tiled_kernel(const PlaceParams p) {
 
 // ------------------------------------------------------------------------------------------------
 // List mode: the pairs the integer fast path declined (too many near-ties, unknown bytes, tables that do
-// not fit its fixed-point range).  The fast kernel files them per work item (organism x chunk of sequences), so
-// a CTA here claims an item that has hand-backs, runs the organism prologue ONCE and lets its warps take the
-// item's pairs in turn.  Items are scanned 32 at a time (one count per lane + ballot).
+// not fit its fixed-point range).  The fast kernel files them per work item (organism x chunk of sequences).
+// list_units_kernel turns the per-item counts into work UNITS of up to kListUnitPairs pairs (exclusive prefix sum over the
+// items); place_list_kernel gives every CTA a CONTIGUOUS range of units, so the work is balanced whatever the
+// distribution of the hand-backs (a few organisms that tie on every sequence, or a pair here and there), and a CTA
+// re-runs the organism prologue only when the organism changes between consecutive units.
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxListBuckets = 24;
+constexpr int kListUnitPairs = 8;
 struct ListBuckets {
   int n;                                  // fast-path launches (tile buckets) of this length class
   int item_begin[kMaxListBuckets + 1];    // first global item of bucket b; [n] = total
@@ -516,36 +656,90 @@ struct ListBuckets {
   long long pair_base[kMaxListBuckets];   // first slot of the bucket in fb_item_seqs
 };
 
+// unit_begin[g] = number of units of the items before g, unit_begin[total_items] = all units; one CTA.
+__global__ void __launch_bounds__(1024) list_units_kernel(const int *__restrict__ fb_item_count, int total_items, int *__restrict__ unit_begin,
+                                                          unsigned long long *fb_total) {
+  __shared__ int s_part[1024];
+  __shared__ long long s_pairs[32];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int per = (total_items + nthr - 1) / nthr;
+  const int lo = min(total_items, tid * per), hi = min(total_items, lo + per);
+  int units = 0;
+  long long pairs = 0;
+  for (int g = lo; g < hi; ++g) {
+    const int c = fb_item_count[g];
+    units += (c + kListUnitPairs - 1) / kListUnitPairs;
+    pairs += c;
+  }
+  s_part[tid] = units;
+  __syncthreads();
+  for (int off = 1; off < nthr; off <<= 1) {  // inclusive scan of the per-thread totals
+    const int add = (tid >= off) ? s_part[tid - off] : 0;
+    __syncthreads();
+    s_part[tid] += add;
+    __syncthreads();
+  }
+  int run = s_part[tid] - units;
+  for (int g = lo; g < hi; ++g) {
+    unit_begin[g] = run;
+    run += (fb_item_count[g] + kListUnitPairs - 1) / kListUnitPairs;
+  }
+  if (tid == nthr - 1) unit_begin[total_items] = s_part[tid];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) pairs += __shfl_xor_sync(0xffffffffu, pairs, o);
+  if ((tid & 31) == 0) s_pairs[tid >> 5] = pairs;
+  __syncthreads();
+  if (tid == 0) {
+    long long all = 0;
+    for (int w = 0; w < (nthr + 31) / 32; ++w) all += s_pairs[w];
+    atomicAdd(fb_total, (unsigned long long)all);
+  }
+}
+
 template <int J, bool TRACE>
 __global__ void __launch_bounds__(128) place_list_kernel(const PlaceParams p, const ListBuckets lb, const int *__restrict__ fb_item_count,
-                                                         const int *__restrict__ fb_item_seqs, unsigned long long *fb_total) {
+                                                         const int *__restrict__ fb_item_seqs, const int *__restrict__ unit_begin) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const ExactSmem sm = carve_exact(p, smem_raw, nwarps);
   double *rows = sm.rows + (size_t)warp * p.nrows * p.row_stride;
   unsigned char *codes = sm.codes + (size_t)warp * p.code_stride;
-  const int total = lb.item_begin[lb.n];
-  int err = 0;
-  for (int g0 = blockIdx.x * 32; g0 < total; g0 += gridDim.x * 32) {
-    const int c = (g0 + lane < total) ? __ldg(fb_item_count + g0 + lane) : 0;
-    unsigned todo = __ballot_sync(0xffffffffu, c > 0);  // the same mask in every warp of the CTA
-    while (todo) {
-      const int bit = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const int g = g0 + bit;
-      const int cnt = __shfl_sync(0xffffffffu, c, bit);
-      int b = 0;
-      while (b + 1 < lb.n && lb.item_begin[b + 1] <= g) ++b;
-      const int item = g - lb.item_begin[b];
-      const int oi = item / lb.chunks[b];
-      const int *seqs = fb_item_seqs + lb.pair_base[b] + (long long)item * lb.spc[b];
-      if (threadIdx.x == 0) atomicAdd(fb_total, (unsigned long long)cnt);
-      __syncthreads();  // the previous item's tables are dead
-      const OrgView v = organism_prologue(p, p.org_list[lb.org_begin[b] + oi], sm.pool, sm.G, sm.rec);
-      __syncthreads();
-      for (int i = warp; i < cnt; i += nwarps)
-        place_pair_exact<J, TRACE>(p, v, __ldg(seqs + i), sm.pool, sm.G, sm.rec, rows, codes, lane, err);
+  const int total_items = lb.item_begin[lb.n];
+  const int total_units = __ldg(unit_begin + total_items);
+  // this CTA's contiguous share of the units
+  const int u_lo = (int)((long long)total_units * blockIdx.x / gridDim.x);
+  const int u_hi = (int)((long long)total_units * (blockIdx.x + 1) / gridDim.x);
+  int err = 0, cur_org = -1;
+  OrgView v;
+  v.o = -1;
+  // item of the first unit: the last g with unit_begin[g] <= u_lo (binary search; later units walk forward)
+  int g = 0;
+  if (u_lo < u_hi) {
+    int a = 0, b = total_items;  // invariant: unit_begin[a] <= u_lo < unit_begin[b]
+    while (b - a > 1) {
+      const int mid = (a + b) >> 1;
+      if (__ldg(unit_begin + mid) <= u_lo) a = mid; else b = mid;
     }
+    g = a;
+  }
+  for (int u = u_lo; u < u_hi; ++u) {
+    while (__ldg(unit_begin + g + 1) <= u) ++g;  // items without hand-backs have no units
+    const int part = u - __ldg(unit_begin + g);
+    const int cnt = __ldg(fb_item_count + g);
+    int b = 0;
+    while (b + 1 < lb.n && lb.item_begin[b + 1] <= g) ++b;
+    const int item = g - lb.item_begin[b];
+    const int o = p.org_list[lb.org_begin[b] + item / lb.chunks[b]];
+    const int *seqs = fb_item_seqs + lb.pair_base[b] + (long long)item * lb.spc[b];
+    if (o != cur_org) {   // uniform over the CTA
+      __syncthreads();    // the previous organism's tables are dead
+      v = organism_prologue(p, o, sm.pool, sm.G, sm.rec);
+      __syncthreads();
+      cur_org = o;
+    }
+    const int first = part * kListUnitPairs, last = min(cnt, first + kListUnitPairs);
+    for (int i = first + warp; i < last; i += nwarps)
+      place_pair_exact<J, TRACE>(p, v, __ldg(seqs + i), sm.pool, sm.G, sm.rec, rows, codes, lane, err);
   }
   if (err) atomicOr(p.err_flag, err);
 }

@@ -117,6 +117,51 @@ class DeviceGather:
         return full
 
 
+class MultiDeviceEvaluator:
+    """ONE process driving every GPU of the box: one Engine (CUDA context + stream) per device, organisms sharded by
+    cost, sequences replicated and kept resident, placement launched asynchronously on all devices before the first
+    result is collected.  This is the shape the GA driver needs -- the population lives in one Python process
+    (src/search_organisms.py holds it in a list) -- and it replaces the reference's mpi4py scatter / gather of pickled
+    organisms (:140-143, :268-277) without replaying the GA on several ranks.  No collective is involved: the host
+    process is the gather point.  (bench.py's one-rank-per-GPU mode uses DeviceGather / NCCL instead.)
+
+        evaluator = MultiDeviceEvaluator()            # all visible devices
+        stats = evaluator(organisms, pos, neg, "Welch", 0.2)      # [n_org, 5], same doubles as a single engine
+    """
+
+    def __init__(self, devices=None):
+        from . import _cabi
+        from .engine import Engine
+        if devices is None:
+            devices = list(range(max(1, _cabi.load_library().fl_device_count())))
+        self.engines = [Engine(d) for d in devices]
+
+    def __call__(self, organisms, pos_sequences, neg_sequences, method: str = "Welch", gamma: float = 0.2) -> np.ndarray:
+        n_dev = len(self.engines)
+        seq_len = max((len(s) for s in pos_sequences), default=1)
+        shards = shard_by_cost(organism_costs(organisms, seq_len), n_dev)
+        full = np.empty((len(organisms), 5))
+        busy = []
+        joined_pos = self.engines[0].join_sequences(pos_sequences)
+        joined_neg = self.engines[0].join_sequences(neg_sequences)
+        for eng, shard in zip(self.engines, shards):      # issue: uploads + asynchronous placement, device by device
+            if not len(shard):
+                continue
+            pos = eng.upload_sequences(pos_sequences, 0, reuse=True, joined=joined_pos)
+            neg = eng.upload_sequences(neg_sequences, 1, reuse=True, joined=joined_neg)
+            eng.upload_population([organisms[i] for i in shard])
+            eng.place(pos, fetch=False)
+            eng.place(neg, fetch=False)
+            busy.append((eng, shard, pos, neg))
+        for eng, shard, pos, neg in busy:                 # collect: the fitness reduction synchronises its device
+            full[shard] = eng.fitness(pos, neg, method, gamma)
+        return full
+
+    def close(self):
+        for eng in self.engines:
+            eng.close()
+
+
 def evaluate_sharded(engine, organisms, pos_sequences, neg_sequences, method: str = "Welch", gamma: float = 0.2,
                      rank: int = 0, world_size: int = 1, device=None, group=None, shards=None, reuse_sets: bool = True,
                      gather: "DeviceGather | None" = None) -> np.ndarray:

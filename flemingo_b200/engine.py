@@ -93,10 +93,13 @@ class Engine:
     def launch_count(self) -> int:
         return int(self._lib.fl_launch_count(self._ctx))
 
-    def path_stats(self) -> tuple[int, int]:
-        """(pairs sent to the integer filter pass, pairs it handed back to the exact kernel) since the last call."""
-        a, b = C.c_longlong(0), C.c_longlong(0)
-        _cabi.check(self._lib.fl_path_stats(self._ctx, C.byref(a), C.byref(b)))
+    def path_stats(self, detail: bool = False):
+        """(pairs sent to the integer filter pass, pairs it handed to the exact kernel in the end) since the last call;
+        detail=True adds the pairs that took the int32 second chance after the packed 16-bit pass."""
+        a, b, c = C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)
+        _cabi.check(self._lib.fl_path_stats(self._ctx, C.byref(a), C.byref(b), C.byref(c)))
+        if detail:
+            return int(a.value), int(b.value), int(c.value)
         return int(a.value), int(b.value)
 
     def measure_dpx_rate(self) -> dict:
@@ -109,23 +112,31 @@ class Engine:
         _cabi.check(self._lib.fl_sync(self._ctx))
 
     # -- uploads --------------------------------------------------------------------------------
-    def upload_sequences(self, sequences, set_id: int = 0, reuse: bool = False) -> SequenceSet:
+    @staticmethod
+    def join_sequences(sequences):
+        """(bytes of all sequences back to back, int64 lengths): what upload_sequences sends; callers that feed several
+        engines with one dataset join it once."""
+        lengths = np.fromiter(map(len, sequences), dtype=np.int64, count=len(sequences))
+        try:
+            joined = "".join(sequences).encode("ascii")          # the common case: a list of str
+        except TypeError:
+            joined = b"".join(s if isinstance(s, (bytes, bytearray)) else bytes(s, "ASCII") for s in sequences)
+        if int(lengths.sum()) != len(joined):
+            raise ValueError("sequences must be ASCII")
+        return joined, lengths
+
+    def upload_sequences(self, sequences, set_id: int = 0, reuse: bool = False, joined=None) -> SequenceSet:
         """Uploads a DNA set (list of str/bytes); bases are 2-bit packed on the way (fl_upload_sequences).
 
         reuse=True skips the upload when the set resident under set_id holds byte-for-byte the same sequences: the
         GA evaluates thousands of generations on one dataset, so the packed copy stays in HBM across calls.
+        joined: the result of join_sequences(sequences), if the caller already has it.
         """
         old = self._sets.get(set_id)
         seqs = sequences
-        lengths = np.fromiter(map(len, seqs), dtype=np.int64, count=len(seqs))
-        try:
-            joined = "".join(seqs).encode("ascii")          # the common case: a list of str
-        except TypeError:
-            joined = b"".join(s if isinstance(s, (bytes, bytearray)) else bytes(s, "ASCII") for s in seqs)
+        joined, lengths = joined if joined is not None else self.join_sequences(seqs)
         offsets = np.zeros(len(seqs) + 1, dtype=np.int64)
         np.cumsum(lengths, out=offsets[1:])
-        if offsets[-1] != len(joined):
-            raise ValueError("sequences must be ASCII")
         if reuse and old is not None and old.n_seq == len(seqs) and old.blob == joined and np.array_equal(old.lengths, lengths):
             return old
         blob = np.frombuffer(joined + b"\0", dtype=np.uint8)

@@ -90,6 +90,10 @@ typedef struct fl_population {
 const char *fl_last_error(void);
 int fl_abi_version(void);
 
+/* CUDA devices visible to this process (0 if there is none or the driver is missing); one context per device lets a
+   single GA driver process feed all GPUs of a box (flemingo_b200.distributed.MultiDeviceEvaluator). */
+int fl_device_count(void);
+
 /* Creates the context on `device` and uploads the data tables (_constants.h:7-11; tables.bin order). */
 int fl_ctx_create(int device, const double *tables, long long n_tables, fl_ctx **out);
 int fl_ctx_destroy(fl_ctx *ctx);
@@ -162,10 +166,11 @@ int fl_calculate(fl_ctx *ctx, const char *sequence, int seq_len, const char *rec
                  const double *bin_freqs, const double *bin_edges, const int *num_bins);
 
 /*
- * Since the last call: pairs routed to the integer filter pass, and how many of those it handed back to the exact
- * kernel (too many near-ties, unknown bytes, tables outside its fixed-point range).  Synchronises.
+ * Since the last call: pairs routed to the integer filter pass; how many of those it handed to the exact kernel in the
+ * end (too many ties, unknown bytes, tables outside its fixed-point range); and how many took the int32 second chance
+ * after the packed 16-bit pass had let too many near-ties through (may be NULL).  Synchronises.
  */
-int fl_path_stats(fl_ctx *ctx, long long *fast_pairs, long long *fallback_pairs);
+int fl_path_stats(fl_ctx *ctx, long long *fast_pairs, long long *fallback_pairs, long long *second_chance_pairs);
 
 /*
  * ---- table builders (host code, no device work, no context) -------------------------------------------------------

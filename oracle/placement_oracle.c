@@ -6,7 +6,7 @@
  * under flemingo_b200/ may include, link or call this file.
  *
  * Parity status: PINNED.  oracle/_ref (the unmodified reference extension, compiled from
- * /root/reference by oracle/Makefile) is run against this restatement by tests/test_oracle_vs_ref.py and
+ * /root/reference by oracle/Makefile) is run against this restatement by tests/test_oracle_golden.py and
  * by tests/golden/make_golden.py; the committed fixtures under tests/golden/ are reference outputs.
  *
  * What it restates (reference file:line, relative to /root/reference/extensions/multiplacement/src):
@@ -162,7 +162,7 @@ int fo_place(const double *tables, const char *seq, int s_len, const char *rec_t
   int n_pos = s_len - sum_len + 1;
   int eff_len = s_len - sum_len + n_rec;
   if (n_rec > 1 && (max_length < 0 || s_len - sum_len > max_length)) return FO_UNSUPPORTED;
-  if (eff_len > 10000) return FO_UNSUPPORTED;
+  if (n_rec > 1 && eff_len > 10000) return FO_UNSUPPORTED;  /* DEN_EXPANSION is only read through a connector */
 
   double *R = (double *)malloc(sizeof(double) * (size_t)n_rec * n_pos);       /* score rows */
   double *C = (double *)malloc(sizeof(double) * (size_t)n_rec * n_pos);       /* cumulative rows, one per stage */

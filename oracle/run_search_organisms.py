@@ -67,6 +67,11 @@ def main():
     ap.add_argument("--fitness", default="Welch")
     ap.add_argument("--max-pos", type=int, default=100)
     ap.add_argument("--max-neg", type=int, default=100)
+    ap.add_argument("--synthetic", default=None, metavar="N_POS,N_NEG,LEN",
+                    help="replace the bundled FASTA files by random-nucleotide datasets of this shape (seeds 1 and 2)")
+    ap.add_argument("--devices", type=int, default=1, help="batched mode: GPUs driven by this one process (MultiDeviceEvaluator)")
+    ap.add_argument("--no-exports", action="store_true", help="no periodic organism / population exports (long runs)")
+    ap.add_argument("--max-recognizers", type=int, default=0, help="organism.MAX_NUM_OF_RECOGNIZERS (0: keep the config's 5)")
     ap.add_argument("--models", default=None, help="a models/models pickle written by an earlier run (skips the ~10 s null-model generation)")
     ap.add_argument("--save-models", default=None, help="copy this run's models/models pickle here")
     args = ap.parse_args()
@@ -74,7 +79,12 @@ def main():
     src_master = HERE / "_ref" / "src"
     if not (src_master / "search_organisms.py").exists():
         sys.exit("oracle/_ref/src is missing: run `make -C oracle refsrc` where /root/reference exists")
-    work = Path(args.workdir)
+    args.out = str(Path(args.out).resolve())
+    if args.models:
+        args.models = str(Path(args.models).resolve())
+    if args.save_models:
+        args.save_models = str(Path(args.save_models).resolve())
+    work = Path(args.workdir).resolve()
     if work.exists():
         shutil.rmtree(work)
     shutil.copytree(src_master, work / "src")
@@ -87,6 +97,20 @@ def main():
         "MIN_ITERATIONS": args.gens, "END_WHILE_METHOD": "iterations", "PERIODIC_ORG_EXPORT": 1, "PERIODIC_POP_EXPORT": 1,
         "GEN_INFO_TO_STDOUT": False, "FITNESS_FUNCTION": args.fitness,
         "MAX_SEQUENCES_TO_FIT_POS": args.max_pos, "MAX_SEQUENCES_TO_FIT_NEG": args.max_neg})
+    if args.synthetic:
+        n_pos, n_neg, seq_len = (int(x) for x in args.synthetic.split(","))
+        import numpy as _np
+        for name, n, seed in (("synthetic_pos.fas", n_pos, 1), ("synthetic_neg.fas", n_neg, 2)):
+            rng = _np.random.default_rng(seed)
+            letters = _np.frombuffer(b"ACGT", dtype=_np.uint8)
+            with open(src / "datasets" / name, "w") as fh:
+                for k, row in enumerate(rng.integers(0, 4, size=(n, seq_len))):
+                    fh.write(f">s{k}\n{letters[row].tobytes().decode()}\n")
+        config["main"].update({"POSITIVE_FILENAME": "synthetic_pos.fas", "NEGATIVE_FILENAME": "synthetic_neg.fas"})
+    if args.no_exports:
+        config["main"].update({"PERIODIC_ORG_EXPORT": 10 ** 9, "PERIODIC_POP_EXPORT": 10 ** 9})
+    if args.max_recognizers:
+        config["organism"]["MAX_NUM_OF_RECOGNIZERS"] = args.max_recognizers
     config["organismFactory"]["PROBABILITY_RECOMBINATION"] = args.recombination
     if args.mle:
         config["organismFactory"]["PERIODIC_MLE"] = args.mle
@@ -126,9 +150,14 @@ def main():
         dropin.accelerate_reference()
     t0 = _time.time()
     so.set_up()
+    ga_times = None
     if args.mode == "batched":
         from flemingo_b200 import ga
-        ga.run(so)
+        evaluator = None
+        if args.devices > 1:
+            from flemingo_b200.distributed import MultiDeviceEvaluator
+            evaluator = MultiDeviceEvaluator(list(range(args.devices)))
+        ga_times = ga.run(so, evaluator=evaluator)[1].as_dict()
     else:
         so.main()
     wall = _time.time() - t0
@@ -144,9 +173,12 @@ def main():
         if path.is_file() and path.name not in ("output.txt", "parameters.txt", "parameters.json"):
             files[str(path.relative_to(rdir))] = hashlib.sha256(path.read_bytes()).hexdigest()
     summary = {"mode": args.mode, "wall_s": wall, "output": lines, "files": files, "default_rng_calls": counter["n"]}
+    if ga_times is not None:
+        summary["generation_times"] = ga_times
     if args.mode != "stock":
         from flemingo_b200.engine import get_engine
-        summary["gpu_launches"] = get_engine().launch_count
+        summary["gpu_launches"] = get_engine().launch_count if args.devices <= 1 or args.mode != "batched" else \
+            sum(e.launch_count for e in evaluator.engines) + get_engine().launch_count
     json.dump(summary, open(args.out, "w"), indent=1)
     print(f"{args.mode}: {len(lines)} generations, {len(files)} exported files, {wall:.1f} s")
 

@@ -12,6 +12,21 @@ using std::min;
 static inline double neg_inf() { return -std::numeric_limits<double>::infinity(); }
 constexpr int kGPad = 32;
 static inline int __viaddmax_s32(int a, int b, int c) { return std::max(a + b, c); }
+// host stand-ins for the packed 16-bit intrinsics of dp_stage16
+static inline short lo16(unsigned x) { return (short)(x & 0xffffu); }
+static inline short hi16(unsigned x) { return (short)(x >> 16); }
+static inline unsigned pack16(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
+static inline unsigned __viaddmax_s16x2(unsigned a, unsigned b, unsigned c) {
+  const short l = (short)(lo16(a) + lo16(b)), h = (short)(hi16(a) + hi16(b));  // wrapping add, like the instruction
+  return pack16(std::max<short>(l, lo16(c)), std::max<short>(h, hi16(c)));
+}
+static inline unsigned __vmaxs2(unsigned a, unsigned b) { return pack16(std::max(lo16(a), lo16(b)), std::max(hi16(a), hi16(b))); }
+static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) {
+  unsigned long long v = ((unsigned long long)b << 32) | a;
+  unsigned r = 0;
+  for (int i = 0; i < 4; i++) r |= (unsigned)((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xff) << (8 * i);
+  return r;
+}
 #include TILE_EXTRACT
 template <int J, int TEAM> int run_i32(int P, unsigned seed) {
   srand(seed);
@@ -74,6 +89,64 @@ template <int J, int TEAM> int run_i32_inplace(int P, unsigned seed) {
   for (int j = 0; j < P; j++) if (buf[j] != ref[j]) bad++;
   return bad;
 }
+// Packed 16-bit stage: H[d] = (G[d], G[d-1]), sentinel outside [0, P-2]; values sized so that nothing wraps.
+template <int J, int TEAM> int run_i16(int P, unsigned seed, bool inplace) {
+  srand(seed);
+  const int SENT = -20000;
+  int NBJ = ((P + J - 1) / J) * J;
+  std::vector<short> prev(NBJ + 64, 0), cur(NBJ + 64, -12345);
+  std::vector<int> G(P + 2 * kGPad + 2, SENT), ref(P);
+  for (int i = 0; i < P; i++) prev[i] = (short)(-(rand() % 6000));
+  for (int i = 0; i + 1 < P; i++) G[kGPad + i] = -(rand() % 6000);   // gap P-1 keeps the sentinel
+  for (int j = 0; j < P; j++) { int b = -32768; for (int k = 0; k <= j; k++) b = std::max(b, prev[k] + G[kGPad + j - k]); ref[j] = b; }
+  std::vector<unsigned> H(P + 2 * kGPad + 2);
+  for (int i = 1; i < (int)H.size(); i++) H[i] = pack16(G[i], G[i - 1]);
+  H[0] = pack16(G[0], SENT);
+  const unsigned *Hp = H.data() + kGPad;
+  if (!inplace) {
+    for (int tl = 0; tl < TEAM; tl++) dp_stage16<J, TEAM>(prev.data(), cur.data(), Hp, P, tl);
+  } else {
+    // lanes in lockstep on ONE buffer, mirroring dp_stage16's control flow (see run_i32_inplace)
+    short *buf = prev.data();
+    const int NB = (P + J - 1) / J;
+    for (int r0 = ((NB - 1) / (2 * TEAM)) * (2 * TEAM); r0 >= 0; r0 -= 2 * TEAM) {
+      const int nbr = std::min(2 * TEAM, NB - r0), half = (nbr + 1) >> 1;
+      TileState st[TEAM];
+      unsigned acc[TEAM][J], A[TEAM][J], B[TEAM][J];
+      for (int tl = 0; tl < TEAM; tl++) {
+        const int bA = r0 + tl, bB = r0 + nbr - 1 - tl;
+        if (tl < half) { st[tl].b = bB; st[tl].kend = bB + 1; st[tl].kstep = 1; st[tl].next_b = (bB > bA) ? bA : -1; }
+        else { st[tl].b = 0; st[tl].kend = -1; st[tl].kstep = 0; st[tl].next_b = -1; }
+        st[tl].kb = 0;
+        const unsigned *ha = Hp + st[tl].b * J + (J - 1);
+        for (int t = 0; t < J; t++) { acc[tl][t] = kLowest16x2; A[tl][t] = ha[-t]; }
+      }
+      const int iters = 2 * r0 + nbr + 1;
+      bool a_role = true;
+      for (int it = 0; it < iters; it++) {
+        const bool last = (it == iters - 1);
+        for (int tl = 0; tl < TEAM; tl++) {
+          if (a_role) tile_switch16<J>(A[tl], acc[tl], st[tl], buf, Hp);
+          else tile_switch16<J>(B[tl], acc[tl], st[tl], buf, Hp);
+        }
+        for (int tl = 0; tl < TEAM; tl++) {
+          if (last) {
+            if (a_role) tile_last16<J>(A[tl], acc[tl], st[tl], buf, buf, Hp);
+            else tile_last16<J>(B[tl], acc[tl], st[tl], buf, buf, Hp);
+          } else if (a_role) tile_step16<J>(A[tl], B[tl], acc[tl], st[tl], buf, buf, Hp);
+          else tile_step16<J>(B[tl], A[tl], acc[tl], st[tl], buf, buf, Hp);
+        }
+        a_role = !a_role;
+      }
+      for (int tl = 0; tl < TEAM; tl++)
+        if (st[tl].kstep) flush16<J>(acc[tl], buf, st[tl].b);
+    }
+    cur = prev;
+  }
+  int bad = 0;
+  for (int j = 0; j < P; j++) if (cur[j] != ref[j]) bad++;
+  return bad;
+}
 template <int J> int run(int P, unsigned seed) {
   srand(seed);
   int NBJ = ((P + J - 1) / J) * J;
@@ -95,6 +168,9 @@ int main() {
     b += run_i32_inplace<17, 8>(P, P + 12) + run_i32_inplace<19, 8>(P, P + 13) + run_i32_inplace<9, 16>(P, P + 14) +
          run_i32_inplace<13, 32>(P, P + 15) + run_i32_inplace<3, 8>(P, P + 16) + run_i32_inplace<21, 16>(P, P + 17) +
          run_i32_inplace<5, 8>(P, P + 18);
+    for (int ip = 0; ip < 2 && P >= 2; ip++)   // P = 1 has no legit gap: the integer pass never sees it (FastPlan.ok)
+      b += run_i16<18, 8>(P, P + 20, ip) + run_i16<14, 8>(P, P + 21, ip) + run_i16<10, 16>(P, P + 22, ip) + run_i16<6, 8>(P, P + 23, ip) +
+           run_i16<22, 32>(P, P + 24, ip) + run_i16<18, 16>(P, P + 25, ip) + run_i16<2, 8>(P, P + 26, ip);
     if (b) printf("P=%d bad=%d\n", P, b);
     total += b;
   }

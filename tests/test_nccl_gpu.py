@@ -69,3 +69,28 @@ def test_two_rank_nccl_sharded_equals_unsharded(tmp_path):
     out = json.loads(result.read_text())
     assert out["Welch"] and out["Yuen"] and out["Trim-left-M-SD"] and out["one_organism"], out
     assert sum(out["shard_sizes"]) == 321 and min(out["shard_sizes"]) > 100
+
+
+def test_single_process_multi_device_evaluator_equals_one_engine():
+    """The GA driver's multi-GPU mode: ONE process, one engine per device (MultiDeviceEvaluator) -- same doubles as a
+    single engine evaluating the whole population."""
+    import torch
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    from flemingo_b200 import synthetic
+    from flemingo_b200.distributed import MultiDeviceEvaluator
+    from flemingo_b200.engine import Engine
+    orgs = synthetic.mixed_organisms(150, 300, 7) + synthetic.pssm_organisms(30, 300, 8)
+    pos = synthetic.random_sequences(200, 300, 1)
+    neg = synthetic.random_sequences(180, 300, 2)
+    multi = MultiDeviceEvaluator([0, 1])
+    one = Engine(0)
+    try:
+        for method, gamma in (("Welch", 0.2), ("Trim-left-M", 0.3)):
+            a = multi(orgs, pos, neg, method, gamma)
+            b = one.evaluate(orgs, pos, neg, method, gamma)
+            assert np.array_equal(a.view(np.int64), b.view(np.int64))
+        assert np.array_equal(multi(orgs[:1], pos, neg), one.evaluate(orgs[:1], pos, neg))   # fewer organisms than devices
+    finally:
+        multi.close()
+        one.close()

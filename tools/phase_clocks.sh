@@ -5,4 +5,4 @@ set -e
 out=${1:-tools}
 mkdir -p "$out/_phase_lib"
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 -shared -Xcompiler -fPIC \
-     -DFL_PHASE_CLOCKS -I include -o "$out/_phase_lib/libflemingo_b200.so" flemingo_b200/csrc/flemingo_b200.cu
+     -DFL_PHASE_CLOCKS -I include -o "$out/_phase_lib/libflemingo_b200.so" flemingo_b200/csrc/flemingo_b200.cu flemingo_b200/csrc/builders.cu
