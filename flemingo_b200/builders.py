@@ -18,8 +18,18 @@ import numpy as np
 from . import _cabi
 
 
+class TableList(list):
+    """A list of immutable numpy scalars (stored_pdfs / stored_cdfs / alt_model) that copy.deepcopy duplicates in one
+    step.  The reference clones every organism with deepcopy (organism_factory.py:893 clone_organism), which otherwise
+    walks the ~2 * max_seq_length float objects of each connector one by one -- 4 ms per clone, the largest host cost of
+    a generation once placement runs on the GPU.  Behaves as a plain list everywhere else (`a + b` gives a list)."""
+
+    def __deepcopy__(self, memo):
+        return TableList(self)
+
+
 def _ptr(a):
-    return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(a.__array_interface__["data"][0])
 
 
 def _check(rc: int, what: str) -> None:
@@ -30,8 +40,8 @@ def _check(rc: int, what: str) -> None:
 def connector_tables(mu, sigma, M: int, pseudo_count: float, n_threads: int = 0):
     """(stored_pdfs[n, M], stored_cdfs[n, M]) of n connectors, log2 like the reference (-inf where its log2 is)."""
     lib = _cabi.load_library()
-    mu = np.ascontiguousarray(np.atleast_1d(mu), dtype=np.float64)
-    sigma = np.ascontiguousarray(np.atleast_1d(sigma), dtype=np.float64)
+    mu = np.array(mu, dtype=np.float64, ndmin=1)
+    sigma = np.array(sigma, dtype=np.float64, ndmin=1)
     n = int(mu.size)
     args = np.empty((2, n, int(M)), dtype=np.float64)
     _check(lib.fl_build_connector_tables(_ptr(mu), _ptr(sigma), n, int(M), float(pseudo_count), _ptr(args[0]), _ptr(args[1]),

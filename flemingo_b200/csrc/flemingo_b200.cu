@@ -114,12 +114,17 @@ static int pick_fast(int P, int bits) {
   int best = -1;
   double best_cost = 1e300;
   // experiments: FLEMINGO_FAST_CFG="J,TEAM" forces one configuration (of the arithmetic that has it)
-  if (const char *force = getenv("FLEMINGO_FAST_CFG")) {
+  static const char *force = getenv("FLEMINGO_FAST_CFG");
+  if (force) {
     int fj = 0, ft = 0;
     if (sscanf(force, "%d,%d", &fj, &ft) == 2)
       for (int i = 0; i < kNumFastConfigs; ++i)
         if (kFastConfigs[i].J == fj && kFastConfigs[i].team == ft && kFastConfigs[i].bits == bits) return i;
   }
+  // the choice depends on (P, bits) only: a ragged dataset asks for every organism of every length class
+  static std::vector<int> cache[2];
+  std::vector<int> &memo = cache[bits == 16 ? 1 : 0];
+  if (P >= 0 && P < (int)memo.size() && memo[P] >= 0) return memo[P];
   for (int i = 0; i < kNumFastConfigs; ++i) {
     if (kFastConfigs[i].bits != bits) continue;
     const double c = fast_cost(P, kFastConfigs[i].J, kFastConfigs[i].team, bits);
@@ -127,6 +132,10 @@ static int pick_fast(int P, int bits) {
       best_cost = c;
       best = i;
     }
+  }
+  if (P >= 0 && P < (1 << 20)) {
+    if (P >= (int)memo.size()) memo.resize(P + 1, -1);
+    memo[P] = best;
   }
   return best;
 }
@@ -193,7 +202,17 @@ struct Population {
 struct fl_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  DevBuf tables, err_flag, con_begin, org_list, gaps, rsc, csc, fit_out, fit_scratch, fb_item_count, fb_item_seqs, fb_unit_begin, fast_scratch, fb_total, fb_retried, work_counters;
+  DevBuf tables, err_flag, con_begin, org_list, gaps, rsc, csc, fit_out, fit_scratch, fb_total, fb_retried;
+  // A dataset with several sequence lengths is placed class by class (one launch chain per length); the chains of
+  // different classes are independent, so they go round-robin onto kLanes streams -- the main stream and kLanes - 1
+  // helpers -- each with its own hand-back lists, row scratch and work counter.  A single-length dataset uses lane 0 only.
+  static constexpr int kLanes = 4;
+  struct Lane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    DevBuf fb_item_count, fb_item_seqs, fb_unit_begin, fast_scratch, work_counter;
+  } lanes[kLanes];
+  cudaEvent_t ready = nullptr;
   int fast_reg_warps[64] = {0};
   std::vector<double> h_den;  // host copy of DEN_EXPANSION (fits_int16)
   long long fast_pairs = 0, fallback_pairs = 0;  // statistics of the last fl_place_batch
@@ -234,7 +253,16 @@ extern "C" int fl_ctx_create(int device, const double *tables, long long n_table
   if (rc == FL_OK) rc = ctx->fb_total.ensure(sizeof(unsigned long long));
   if (rc == FL_OK) rc = ctx->fb_retried.ensure(sizeof(unsigned long long));
   if (rc == FL_OK && cudaMemsetAsync(ctx->fb_retried.p, 0, sizeof(unsigned long long), ctx->stream) != cudaSuccess) rc = fail(FL_E_CUDA, "memset failed");
-  if (rc == FL_OK) rc = ctx->work_counters.ensure(1024 * sizeof(int));
+  for (int l = 0; l < fl_ctx::kLanes && rc == FL_OK; ++l) {
+    fl_ctx::Lane &ln = ctx->lanes[l];
+    if (l == 0)
+      ln.stream = ctx->stream;
+    else if (cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking) != cudaSuccess)
+      rc = fail(FL_E_CUDA, "cudaStreamCreate failed");
+    if (rc == FL_OK && cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming) != cudaSuccess) rc = fail(FL_E_CUDA, "cudaEventCreate failed");
+    if (rc == FL_OK) rc = ln.work_counter.ensure(sizeof(int));
+  }
+  if (rc == FL_OK && cudaEventCreateWithFlags(&ctx->ready, cudaEventDisableTiming) != cudaSuccess) rc = fail(FL_E_CUDA, "cudaEventCreate failed");
   if (rc == FL_OK && cudaMemsetAsync(ctx->fb_total.p, 0, sizeof(unsigned long long), ctx->stream) != cudaSuccess) rc = fail(FL_E_CUDA, "memset failed");
   if (rc != FL_OK) {
     delete ctx;
@@ -279,8 +307,15 @@ extern "C" int fl_ctx_destroy(fl_ctx *ctx) {
   }
   release_pop(ctx->pop);
   release_pop(ctx->scratch_pop);
-  DevBuf *bufs[] = {&ctx->tables, &ctx->err_flag, &ctx->con_begin, &ctx->org_list, &ctx->gaps, &ctx->rsc, &ctx->csc, &ctx->fit_out, &ctx->fit_scratch, &ctx->fb_item_count, &ctx->fb_item_seqs, &ctx->fb_unit_begin, &ctx->fast_scratch, &ctx->fb_total, &ctx->fb_retried, &ctx->work_counters};
+  DevBuf *bufs[] = {&ctx->tables, &ctx->err_flag, &ctx->con_begin, &ctx->org_list, &ctx->gaps, &ctx->rsc, &ctx->csc, &ctx->fit_out, &ctx->fit_scratch, &ctx->fb_total, &ctx->fb_retried};
   for (DevBuf *b : bufs) b->release();
+  for (fl_ctx::Lane &ln : ctx->lanes) {
+    cudaStreamSynchronize(ln.stream);
+    ln.fb_item_count.release(); ln.fb_item_seqs.release(); ln.fb_unit_begin.release(); ln.fast_scratch.release(); ln.work_counter.release();
+    if (ln.done) cudaEventDestroy(ln.done);
+    if (ln.stream && ln.stream != ctx->stream) cudaStreamDestroy(ln.stream);
+  }
+  if (ctx->ready) cudaEventDestroy(ctx->ready);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return FL_OK;
@@ -586,8 +621,8 @@ extern "C" int fl_update_connectors(fl_ctx *ctx, const double *con_pool, long lo
 // the spread of the combinatorial term den(g) (connector.c:51-56).  True when the packed 16-bit integer pass will
 // accept the organism at a scale of at least 32 units per energy unit (the device re-derives the plan from the real
 // ranges and hands the organism's pairs to the exact kernel should it disagree).
-static bool fits_int16(fl_ctx *ctx, const Population &P, int o, int S, std::map<long long, double> &den_cache) {
-  if (const char *force = getenv("FLEMINGO_FAST_BITS")) return atoi(force) == 16;
+static bool fits_int16(fl_ctx *ctx, const Population &P, int o, int S, std::map<long long, double> &den_cache, const char *force) {
+  if (force) return atoi(force) == 16;
   const int rb = P.rec_begin[o], n = P.rec_begin[o + 1] - rb;
   if (n < 2 || !P.pssm_only[o]) return false;
   const int Pn = S - P.sum_len[o] + 1, eff = S - P.sum_len[o] + n;
@@ -695,8 +730,17 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
     set.bins_signature = P.class_signature;
   }
 
+  const char *env_bits = getenv("FLEMINGO_FAST_BITS");   // experiments / tests: force one arithmetic (read at every call)
+  // several length classes: their launch chains are independent and go round-robin onto the lanes
+  const int n_lanes = n_cls > 1 ? fl_ctx::kLanes : 1;
+  if (n_lanes > 1) {
+    CK(cudaEventRecord(ctx->ready, ctx->stream));
+    for (int l = 1; l < n_lanes; ++l) CK(cudaStreamWaitEvent(ctx->lanes[l].stream, ctx->ready, 0));
+  }
   for (int c = 0; c < n_cls; ++c) {
     const SeqClass &cl = set.classes[c];
+    fl_ctx::Lane &lane = ctx->lanes[c % n_lanes];
+    const cudaStream_t st = lane.stream;
     PlaceParams pp;
     pp.rec_begin = P.d_rec_begin.as<int>();
     pp.rec_type = P.d_rec_type.as<char>();
@@ -762,7 +806,7 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
     for (int o = 0; o < n_org; ++o) {
       const int Po = cl.len - P.sum_len[o] + 1;
       if (allow_fast && P.kmer_need[o] > 0 && P.kmer_need[o] <= 16384 && Po >= 2) {
-        fast_bucket[pick_fast(Po, fits_int16(ctx, P, o, cl.len, den_cache) ? 16 : 32)].push_back(o);
+        fast_bucket[pick_fast(Po, fits_int16(ctx, P, o, cl.len, den_cache, env_bits) ? 16 : 32)].push_back(o);
         kmer_cap = std::max(kmer_cap, P.kmer_need[o]);
         ++n_fast_org;
       } else {
@@ -800,8 +844,12 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
         // slot stride in 32-bit words = TEAM (mod 32), so that the teams of a warp work on disjoint banks
         const int slot_words = ((rows * fast_rowq[j] * elem / 4 + 31) & ~31) + (team & 31);
         const int slot = slot_words * 4 / elem;                   // in row elements
+        // a small length class (a ragged dataset has many) cannot fill a 16-warp CTA: size the CTA for one round of the
+        // class and let several organisms' CTAs share the SM instead
+        const int need_w = std::max(4, (((cl.count + nt - 1) / nt) + 3) & ~3);
         for (int nw : kWarpChoices) {
           if (force_w && atoi(force_w) != nw) continue;
+          if (!force_w && nw > need_w && nw > 4) continue;
           const int cand_w = cand_per_warp(kFastConfigs[j].bits, nt);
           const size_t d = (size_t)pp.pool_stride + (size_t)(P.max_rec - 1) * pp.g_stride + 2ull * nw * P.max_rec * cand_w;
           const size_t i = (size_t)(P.max_rec - 1) * fp.gq_stride + fp.kmer_cap + (size_t)nw * nt * slot_words +
@@ -846,7 +894,7 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
       list.insert(list.end(), fast_bucket[j].begin(), fast_bucket[j].end());
     }
     int *d_list = ctx->org_list.as<int>() + (size_t)c * n_org;
-    CK(cudaMemcpyAsync(d_list, list.data(), (size_t)n_org * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_list, list.data(), (size_t)n_org * 4, cudaMemcpyHostToDevice, st));
     const long long target_ctas = (long long)n_sm * 16;
     for (int j = 0; j < kNumTileSizes; ++j) {
       const int n_b = (int)exact_bucket[j].size();
@@ -861,7 +909,7 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
       pp.chunks = (cl.count + spc - 1) / spc;
       const long long grid = (long long)n_b * pp.chunks;
       if (grid > 0x7fffffffLL) return fail(FL_E_UNSUPPORTED, "grid too large");
-      kPlaceKernels[j][trace ? 1 : 0]<<<(unsigned)grid, nwarps * 32, smem, ctx->stream>>>(pp);
+      kPlaceKernels[j][trace ? 1 : 0]<<<(unsigned)grid, nwarps * 32, smem, st>>>(pp);
       CK(cudaGetLastError());
       ctx->launches++;
     }
@@ -947,13 +995,13 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
         ++lb.n;
       }
       const int list_items = lb.item_begin[lb.n];
-      if ((rc = ctx->fb_item_count.ensure((size_t)total_items * 4 + 4)) || (rc = ctx->fb_item_seqs.ensure((size_t)pair_slots * 4 + 4)) ||
-          (rc = ctx->fast_scratch.ensure((size_t)scratch_ints * 4)))
+      if ((rc = lane.fb_item_count.ensure((size_t)total_items * 4 + 4)) || (rc = lane.fb_item_seqs.ensure((size_t)pair_slots * 4 + 4)) ||
+          (rc = lane.fast_scratch.ensure((size_t)scratch_ints * 4)))
         return rc;
-      CK(cudaMemsetAsync(ctx->fb_item_count.p, 0, (size_t)total_items * 4, ctx->stream));
-      fp.fb_item_count = ctx->fb_item_count.as<int>();
-      fp.fb_item_seqs = ctx->fb_item_seqs.as<int>();
-      fp.scratch = ctx->fast_scratch.as<int>();
+      CK(cudaMemsetAsync(lane.fb_item_count.p, 0, (size_t)total_items * 4, st));
+      fp.fb_item_count = lane.fb_item_count.as<int>();
+      fp.fb_item_seqs = lane.fb_item_seqs.as<int>();
+      fp.scratch = lane.fast_scratch.as<int>();
       fp.retried_total = ctx->fb_retried.as<unsigned long long>();
       for (size_t b = 0; b < geo.size(); ++b) {
         const Geo &g = geo[b];
@@ -976,13 +1024,13 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
           fp.retry_count = fp.fb_item_count + geo[g.retry_of].item_base;
           fp.retry_seqs = fp.fb_item_seqs + geo[g.retry_of].pair_base;
         }
-        fp.work_counter = ctx->work_counters.as<int>() + (ctx->launches % 1024);
-        CK(cudaMemsetAsync(fp.work_counter, 0, sizeof(int), ctx->stream));
+        fp.work_counter = lane.work_counter.as<int>();   // one per lane: launches of a lane run in stream order
+        CK(cudaMemsetAsync(fp.work_counter, 0, sizeof(int), st));
         if (getenv("FLEMINGO_DEBUG_LAUNCH"))
           fprintf(stderr, "fast launch%s: cfg bits=%d J=%d team=%d warps=%d ctas/sm=%d grid=%lld items=%lld spc=%d smem=%zu rows=%d\n",
                   g.retry_of >= 0 ? " (second chance)" : "", kFastConfigs[j].bits, kFastConfigs[j].J, kFastConfigs[j].team, nw,
                   fast_ctas_per_sm[j], g.grid, g.items, g.spc, fast_smem[j], fast_single[j] ? 1 : 2);
-        kFastConfigs[j].fn<<<(unsigned)g.grid, nw * 32, fast_smem[j], ctx->stream>>>(fp);
+        kFastConfigs[j].fn<<<(unsigned)g.grid, nw * 32, fast_smem[j], st>>>(fp);
         CK(cudaGetLastError());
         ctx->launches++;
       }
@@ -998,17 +1046,23 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
         if (lsmem <= (size_t)kMaxSmem / 2 || lw == 1) break;
       }
       if (lsmem > (size_t)kMaxSmem) return fail(FL_E_UNSUPPORTED, "list-mode placement needs %zu bytes of shared memory (limit %d)", lsmem, kMaxSmem);
-      if ((rc = ctx->fb_unit_begin.ensure(((size_t)list_items + 1) * 4))) return rc;
+      if ((rc = lane.fb_unit_begin.ensure(((size_t)list_items + 1) * 4))) return rc;
       const int *list_count = fp.fb_item_count + list_item_base;
-      list_units_kernel<<<1, 1024, 0, ctx->stream>>>(list_count, list_items, ctx->fb_unit_begin.as<int>(),
+      list_units_kernel<<<1, 1024, 0, st>>>(list_count, list_items, lane.fb_unit_begin.as<int>(),
                                                      ctx->fb_total.as<unsigned long long>());
       CK(cudaGetLastError());
       const int list_ctas_per_sm = std::max(1, std::min(4, (int)(233472 / (lsmem + 1024))));
       const unsigned lgrid = (unsigned)((long long)n_sm * list_ctas_per_sm);
-      kListKernels[pick_tile(Pmax)][trace ? 1 : 0]<<<lgrid, lw * 32, lsmem, ctx->stream>>>(lp, lb, list_count, fp.fb_item_seqs,
-                                                                                          ctx->fb_unit_begin.as<int>());
+      kListKernels[pick_tile(Pmax)][trace ? 1 : 0]<<<lgrid, lw * 32, lsmem, st>>>(lp, lb, list_count, fp.fb_item_seqs,
+                                                                                          lane.fb_unit_begin.as<int>());
       CK(cudaGetLastError());
       ctx->launches += 2;
+    }
+  }
+  if (n_lanes > 1) {  // the main stream continues after every lane has finished
+    for (int l = 1; l < n_lanes; ++l) {
+      CK(cudaEventRecord(ctx->lanes[l].done, ctx->lanes[l].stream));
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->lanes[l].done, 0));
     }
   }
   set.E_n_org = n_org;

@@ -1115,7 +1115,9 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
     bool nan_hit = false;
     int row_max = -0x7fffffff - 1;  // this lane's share of the maximum of the row written last
     // ---- phase 1: integer pass ---------------------------------------------------------------------
-    if (plan.ok) {
+    // (skipped when every pair of the warp's round is declined up front -- sequences with unknown bytes; a second-chance
+    // launch over such data would otherwise repeat the work the first launch already wasted)
+    if (plan.ok && !__all_sync(0xffffffffu, decline)) {
       {  // the sequence's 4-mer codes, precomputed at upload: one 16-byte cp.async per chunk
         const unsigned char *src = p.k8g + 16ull * (unsigned long long)p.k8_off[seq];
         for (int c = tl; c < (f.k8_stride >> 4); c += TEAM) cp_async16(k8 + 16 * c, src + 16 * c);

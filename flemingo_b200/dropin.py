@@ -61,8 +61,8 @@ def accelerate_builders(connector_cls=None, pssm_cls=None, shape_cls=None) -> No
     if connector_cls is not None:
         def set_precomputed_pdfs_cdfs(self) -> None:
             pdfs, cdfs = builders.connector_tables([self._mu], [self._sigma], self.max_seq_length, self.pseudo_count, n_threads=1)
-            self.stored_pdfs = list(pdfs[0])
-            self.stored_cdfs = list(cdfs[0])
+            self.stored_pdfs = builders.TableList(pdfs[0])    # lists, as in the reference; deep-copied in one step
+            self.stored_cdfs = builders.TableList(cdfs[0])
 
         connector_cls.set_precomputed_pdfs_cdfs = set_precomputed_pdfs_cdfs
 
@@ -80,7 +80,7 @@ def accelerate_builders(connector_cls=None, pssm_cls=None, shape_cls=None) -> No
                 self._mu = self.min_mu
             elif self._mu > self.max_mu:
                 self._mu = self.max_mu
-            self.alt_model = list(builders.shape_alt_models([self._mu], [self._sigma], [self.edges], self.pseudo_count)[0])
+            self.alt_model = builders.TableList(builders.shape_alt_models([self._mu], [self._sigma], [self.edges], self.pseudo_count)[0])
 
         shape_cls.set_alt_model = set_alt_model
 

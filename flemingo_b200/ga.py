@@ -24,6 +24,7 @@ import time
 import numpy as np
 
 from .engine import get_engine
+from .formats import gini_RSV
 from .objects import build_placement
 
 
@@ -95,11 +96,12 @@ def breed_pair(so, factory, parent1, parent2, generation, positive_dataset, plac
     return pairs
 
 
-def run(so, evaluator=None, times: GenerationTimes | None = None):
+def run(so, evaluator=None, times: GenerationTimes | None = None, placer=None):
     """Batched equivalent of search_organisms.main(); `so` is the reference's module after set_up().
 
     evaluator(organisms, pos, neg, method, gamma) -> [n, 5] overrides the single-GPU engine (multi-GPU:
-    flemingo_b200.distributed.MultiDeviceEvaluator)."""
+    flemingo_b200.distributed.MultiDeviceEvaluator); placer(parents, dna_set, placement_cls) -> placements[parent][seq]
+    overrides place_parents (the CPU test of this loop plugs the reference's own methods into both)."""
     from objects.organism_factory import OrganismFactory
     from objects.placement_object import PlacementObject
 
@@ -144,7 +146,7 @@ def run(so, evaluator=None, times: GenerationTimes | None = None):
         placements_of = None
         if (generation + 1) % factory.periodic_mle == 0:
             parents = population[:2 * n_pairs]
-            placed = place_parents(parents, pos_fit, PlacementObject)
+            placed = (placer or place_parents)(parents, pos_fit, PlacementObject)
             placements_of = {id(p): rows for p, rows in zip(parents, placed)}
         contests = []                                   # (population slot, parent, child) in the reference's order
         for pair in range(n_pairs):
@@ -171,7 +173,9 @@ def run(so, evaluator=None, times: GenerationTimes | None = None):
         # ---- report (:280-360): statistics, the two printed placements, periodic exports ---------------------------------
         mean_fitness = np.mean(pop_fitness_list)
         standard_dev_fitness = np.std(pop_fitness_list)
-        gini_fitness = so.gini_RSV(pop_fitness_list)
+        # the reference's gini_RSV (:1095-1142) is a double loop over the population -- 16.8 M iterations at 4096
+        # organisms, more than a generation's placements take on the GPU; same statistic in O(N log N)
+        gini_fitness = gini_RSV(pop_fitness_list)
         mean_n_rec = np.mean(pop_n_recogs_list)
         idx_of_max_org = np.argmax(pop_fitness_list)
         max_org = population[idx_of_max_org]

@@ -192,8 +192,8 @@ class ConnectorObject:
         # Phi point by point with libm erf in the library (fl_build_connector_tables), log2 by numpy: bit-identical
         # to the reference's scalar loop (tests/test_builders_cpu.py, golden flat arrays)
         pdfs, cdfs = builders.connector_tables([self._mu], [self._sigma], self.max_seq_length, self.pseudo_count, n_threads=1)
-        self.stored_pdfs = list(pdfs[0])
-        self.stored_cdfs = list(cdfs[0])
+        self.stored_pdfs = builders.TableList(pdfs[0])
+        self.stored_cdfs = builders.TableList(cdfs[0])
 
     def adjust_scores(self, c_scores, sequence_length, sum_recognizer_lengths):
         rescale_connector_block(c_scores, self._mu, self._sigma, self.pseudo_count, self.max_seq_length,

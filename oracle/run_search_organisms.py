@@ -13,6 +13,8 @@ modes
                reference's OrganismObject become one batched device call each, table builders run in the library
   batched      accelerated + the driver's generation loop replaced by flemingo_b200.ga.run (all children first, ONE
                device call per generation, competitions afterwards)
+  batched-cpu  flemingo_b200.ga.run on the STOCK reference (its own C extension and fitness code plugged in as the
+               evaluator): checks, without a GPU, that the three-phase loop reproduces the sequential one
 
 What makes two runs comparable: `random` and `numpy.random` are seeded, `numpy.random.default_rng()` (called without a
 seed by connector_object.py:169-173 and shape_object.py:134-138) is replaced by a seeded sequence of generators, and
@@ -56,7 +58,7 @@ class _CountingTime:
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--mode", required=True, choices=["stock", "dropin", "accelerated", "batched"])
+    ap.add_argument("--mode", required=True, choices=["stock", "dropin", "accelerated", "batched", "batched-cpu"])
     ap.add_argument("--workdir", required=True)
     ap.add_argument("--out", required=True)
     ap.add_argument("--pop", type=int, default=16)
@@ -122,7 +124,7 @@ def main():
     sys.path.insert(0, str(src))
     if str(REPO) not in sys.path:
         sys.path.insert(0, str(REPO))
-    if args.mode == "stock":
+    if args.mode in ("stock", "batched-cpu"):
         sys.path.insert(0, str(HERE / "_ref"))           # the compiled reference `_multiplacement`
     else:
         from flemingo_b200 import dropin
@@ -151,7 +153,23 @@ def main():
     t0 = _time.time()
     so.set_up()
     ga_times = None
-    if args.mode == "batched":
+    if args.mode == "batched-cpu":
+        # the batched generation loop on the STOCK reference (CPU): its three phases must reproduce the sequential loop
+        import numpy as _np
+        from flemingo_b200 import ga
+
+        def cpu_evaluator(organisms, pos, neg, method, gamma):
+            rows = _np.zeros((len(organisms), 5))
+            for k, org in enumerate(organisms):
+                org.set_fitness(pos, neg, method, gamma)
+                rows[k, 0] = org.fitness
+            return rows
+
+        def cpu_placer(parents, dna_set, placement_cls):
+            return [[p.get_placement(seq) for seq in dna_set] for p in parents]
+
+        ga_times = ga.run(so, evaluator=cpu_evaluator, placer=cpu_placer)[1].as_dict()
+    elif args.mode == "batched":
         from flemingo_b200 import ga
         evaluator = None
         if args.devices > 1:
@@ -175,7 +193,7 @@ def main():
     summary = {"mode": args.mode, "wall_s": wall, "output": lines, "files": files, "default_rng_calls": counter["n"]}
     if ga_times is not None:
         summary["generation_times"] = ga_times
-    if args.mode != "stock":
+    if args.mode not in ("stock", "batched-cpu"):
         from flemingo_b200.engine import get_engine
         summary["gpu_launches"] = get_engine().launch_count if args.devices <= 1 or args.mode != "batched" else \
             sum(e.launch_count for e in evaluator.engines) + get_engine().launch_count

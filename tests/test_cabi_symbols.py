@@ -24,7 +24,7 @@ def test_library_loads_and_exports_header_symbols():
     assert declared == sorted(_cabi.EXPORTED)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.fl_abi_version() == 1
+    assert lib.fl_abi_version() == 2
     out = subprocess.run(["nm", "-D", "--defined-only", str(_cabi.LIB_PATH)], capture_output=True, text=True).stdout
     exported = sorted(set(re.findall(r" T (fl_[a-z_0-9]+)", out)))
     assert exported == declared

@@ -50,6 +50,13 @@ def test_stock_runs_are_reproducible(tmp_path):
     _assert_same_run(a, b)
 
 
+def test_batched_generation_loop_equals_sequential_loop_on_cpu(tmp_path):
+    """flemingo_b200.ga.run (breed everything, evaluate everything, then select) with the reference's own CPU code as
+    evaluator and placer reproduces search_organisms.main() -- MLE generations and recombination included."""
+    extra = ("--gens", "4", "--pop", "12", "--mle", "2", "--recombination", "0.5", "--seed", "5")
+    _assert_same_run(_run("stock", tmp_path, "cpu", extra), _run("batched-cpu", tmp_path, "cpu", extra))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("scenario,extra", [
     ("plain", ("--gens", "3", "--pop", "16")),
