@@ -624,7 +624,8 @@ extern "C" int fl_update_connectors(fl_ctx *ctx, const double *con_pool, long lo
 static bool fits_int16(fl_ctx *ctx, const Population &P, int o, int S, std::map<long long, double> &den_cache, const char *force) {
   if (force) return atoi(force) == 16;
   const int rb = P.rec_begin[o], n = P.rec_begin[o + 1] - rb;
-  if (n < 2 || !P.pssm_only[o]) return false;
+  static const bool shapes_too = getenv("FLEMINGO_16_SHAPES") != nullptr;   // experiment knob (see the comment above)
+  if (n < 2 || (!P.pssm_only[o] && !shapes_too)) return false;
   const int Pn = S - P.sum_len[o] + 1, eff = S - P.sum_len[o] + n;
   if (Pn < 2 || eff > 10000) return false;
   const long long key = ((long long)n << 32) | (unsigned)P.sum_len[o];
@@ -835,6 +836,7 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
       // multiples of four only: the DP stages are bound by the ALU pipe of each of the SM's four schedulers, so a
       // scheduler that holds one warp more than the others sets the pace (13 warps: 194 ms on config 3, 12 warps: 169 ms)
       static const int kWarpChoices[] = {16, 12, 8, 4, 2, 1};
+      const int max_warps = 16;
       const char *force_w = getenv("FLEMINGO_FAST_WARPS");
       // two quantised rows per pair (ping-pong; the refinement prefetches older rows behind its scans) unless ONE row
       // (in-place stages, older rows fetched on demand) lets more warps live on the SM
@@ -848,6 +850,7 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
         // class and let several organisms' CTAs share the SM instead
         const int need_w = std::max(4, (((cl.count + nt - 1) / nt) + 3) & ~3);
         for (int nw : kWarpChoices) {
+          if (nw > max_warps) continue;
           if (force_w && atoi(force_w) != nw) continue;
           if (!force_w && nw > need_w && nw > 4) continue;
           const int cand_w = cand_per_warp(kFastConfigs[j].bits, nt);
@@ -861,7 +864,7 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
           // whole CTAs only; one large CTA beats several small ones at equal occupancy (the plan and the prologue are
           // paid per CTA and the hardware scheduler favours one CTA's warps), and more than 16 resident warps bought
           // with small CTAs measured slower (packed kernel on config 2: 5 CTAs of 4 warps 1.82 ms per launch, 1 CTA of 16 warps 1.39 ms)
-          const int occ = std::min(16, nw * std::min(ctas, reg_warps / nw)) * 64 + nw;
+          const int occ = std::min(max_warps, nw * std::min(ctas, reg_warps / nw)) * 64 + nw;
           if (occ > best_occ) {
             best_occ = occ;
             fast_warps[j] = nw;

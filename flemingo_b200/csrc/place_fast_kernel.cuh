@@ -1043,6 +1043,8 @@ __device__ __forceinline__ void add_scores_q(const FastPlan &plan, int r, const 
 // placed by a team of TEAM lanes with J x J register tiles of DPX cells.
 // ------------------------------------------------------------------------------------------------
 
+// (20 warps per CTA for the packed kernel -- its rows are half as large -- were measured: launch bound 640 squeezes it to
+// 86 registers and config 2 takes 2.98 ms instead of 2.85-2.90 ms with 16 warps.)
 template <int J, int TEAM, int BITS>
 __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
   constexpr int NT = 32 / TEAM;
@@ -1092,6 +1094,7 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
   build_fast_plan<BITS, RowT>(f, v, sm, warp, lane, nwarps);
   __syncthreads();
   PHASE_MARK(1);
+
   const FastPlan &plan = *sm.plan;
   const int n = v.n, P = v.P;
   const int slot = warp * NT + team;

@@ -33,6 +33,8 @@ def build(ref: bool = True) -> None:
     subprocess.run(["make", "-s", "-C", str(HERE), "oracle"], check=True)
     if ref and Path("/root/reference/extensions/multiplacement/src/_interface.c").exists():
         subprocess.run(["make", "-s", "-C", str(HERE), "ref"], check=True)
+        # the reference's Python driver and objects for the end-to-end GA tests (git-ignored copy, see the Makefile)
+        subprocess.run(["make", "-s", "-C", str(HERE), "refsrc"], check=True)
 
 
 _lib = None
