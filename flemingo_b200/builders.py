@@ -22,10 +22,30 @@ class TableList(list):
     """A list of immutable numpy scalars (stored_pdfs / stored_cdfs / alt_model) that copy.deepcopy duplicates in one
     step.  The reference clones every organism with deepcopy (organism_factory.py:893 clone_organism), which otherwise
     walks the ~2 * max_seq_length float objects of each connector one by one -- 4 ms per clone, the largest host cost of
-    a generation once placement runs on the GPU.  Behaves as a plain list everywhere else (`a + b` gives a list)."""
+    a generation once placement runs on the GPU.  Behaves as a plain list everywhere else (`a + b` gives a list).
+    `np` is the same table as a float64 array (never written to), which lets flatten() concatenate arrays instead of
+    converting lists."""
+
+    np = None
+
+    @classmethod
+    def of(cls, array):
+        out = cls(array)
+        out.np = array
+        return out
 
     def __deepcopy__(self, memo):
-        return TableList(self)
+        out = TableList(self)
+        out.np = self.np
+        return out
+
+
+def as_array(table) -> "np.ndarray":
+    """float64 array of a table attribute: its array twin if it is a TableList that has one, else a conversion."""
+    twin = getattr(table, "np", None)
+    if twin is not None and len(twin) == len(table):
+        return twin
+    return np.array(table, dtype=np.float64)
 
 
 def _ptr(a):

@@ -15,6 +15,7 @@ import sys
 
 from . import multiplacement
 from .engine import get_engine
+from .flatten import flatten_organism
 
 
 def install() -> None:
@@ -61,8 +62,8 @@ def accelerate_builders(connector_cls=None, pssm_cls=None, shape_cls=None) -> No
     if connector_cls is not None:
         def set_precomputed_pdfs_cdfs(self) -> None:
             pdfs, cdfs = builders.connector_tables([self._mu], [self._sigma], self.max_seq_length, self.pseudo_count, n_threads=1)
-            self.stored_pdfs = builders.TableList(pdfs[0])    # lists, as in the reference; deep-copied in one step
-            self.stored_cdfs = builders.TableList(cdfs[0])
+            self.stored_pdfs = builders.TableList.of(pdfs[0])    # lists, as in the reference; deep-copied in one step
+            self.stored_cdfs = builders.TableList.of(cdfs[0])
 
         connector_cls.set_precomputed_pdfs_cdfs = set_precomputed_pdfs_cdfs
 
@@ -71,6 +72,9 @@ def accelerate_builders(connector_cls=None, pssm_cls=None, shape_cls=None) -> No
             vals = builders.pssm_values(np.array([[col["c"], col["t"], col["g"], col["a"]] for col in self.pwm], dtype=np.float64),
                                         self.pseudo_count)
             self.pssm = np.array([{"c": float(r[0]), "t": float(r[1]), "g": float(r[2]), "a": float(r[3])} for r in vals])
+            # the same values in flatten()'s order (a, g, c, t per column), valid as long as self.pssm is this object
+            self._pssm_flat = np.ascontiguousarray(vals[:, [3, 2, 0, 1]]).ravel()
+            self._pssm_src = self.pssm
 
         pssm_cls.recalculate_pssm = recalculate_pssm
 
@@ -80,7 +84,7 @@ def accelerate_builders(connector_cls=None, pssm_cls=None, shape_cls=None) -> No
                 self._mu = self.min_mu
             elif self._mu > self.max_mu:
                 self._mu = self.max_mu
-            self.alt_model = builders.TableList(builders.shape_alt_models([self._mu], [self._sigma], [self.edges], self.pseudo_count)[0])
+            self.alt_model = builders.TableList.of(builders.shape_alt_models([self._mu], [self._sigma], [self.edges], self.pseudo_count)[0])
 
         shape_cls.set_alt_model = set_alt_model
 
@@ -95,3 +99,4 @@ def accelerate_reference() -> None:
     from objects.shape_object import ShapeObject
     accelerate(OrganismObject)
     accelerate_builders(ConnectorObject, PssmObject, ShapeObject)
+    OrganismObject.flatten = flatten_organism

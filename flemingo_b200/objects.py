@@ -24,6 +24,7 @@ import numpy as np
 
 from . import builders
 from . import multiplacement as _multiplacement
+from .flatten import flatten_organism
 from .engine import get_engine
 from .population import rescale_connector_block
 
@@ -97,6 +98,8 @@ class PssmObject:
         vals = builders.pssm_values(np.array([[column[b] for b in ("c", "t", "g", "a")] for column in self.pwm], dtype=np.float64),
                                     self.pseudo_count)
         self.pssm = np.array([{"c": float(r[0]), "t": float(r[1]), "g": float(r[2]), "a": float(r[3])} for r in vals])
+        self._pssm_flat = np.ascontiguousarray(vals[:, [3, 2, 0, 1]]).ravel()   # flatten()'s order: a, g, c, t per column
+        self._pssm_src = self.pssm
 
     def get_type(self):
         return 'p'
@@ -148,7 +151,7 @@ class ShapeObject:
             self._mu = self.min_mu
         elif self._mu > self.max_mu:
             self._mu = self.max_mu
-        self.alt_model = list(builders.shape_alt_models([self._mu], [self._sigma], [self.edges], self.pseudo_count)[0])
+        self.alt_model = builders.TableList.of(builders.shape_alt_models([self._mu], [self._sigma], [self.edges], self.pseudo_count)[0])
 
     def get_type(self):
         return self._TYPE_CHAR.get(self.type)
@@ -192,8 +195,8 @@ class ConnectorObject:
         # Phi point by point with libm erf in the library (fl_build_connector_tables), log2 by numpy: bit-identical
         # to the reference's scalar loop (tests/test_builders_cpu.py, golden flat arrays)
         pdfs, cdfs = builders.connector_tables([self._mu], [self._sigma], self.max_seq_length, self.pseudo_count, n_threads=1)
-        self.stored_pdfs = builders.TableList(pdfs[0])
-        self.stored_cdfs = builders.TableList(cdfs[0])
+        self.stored_pdfs = builders.TableList.of(pdfs[0])
+        self.stored_cdfs = builders.TableList.of(cdfs[0])
 
     def adjust_scores(self, c_scores, sequence_length, sum_recognizer_lengths):
         rescale_connector_block(c_scores, self._mu, self._sigma, self.pseudo_count, self.max_seq_length,
@@ -228,36 +231,7 @@ class OrganismObject:
         self.sum_recognizer_lengths = sum([i.length for i in self.recognizers])
 
     def flatten(self) -> None:
-        pssm_vals, models, edges, bin_nums, lengths = [], [], [], [], []
-        types = ""
-        for rec in self.recognizers:
-            kind = rec.get_type()
-            if kind == 'p':
-                for column in rec.pssm:
-                    pssm_vals.extend(column[b] for b in ('a', 'g', 'c', 't'))
-            else:
-                models.extend(rec.null_model)
-                models.extend(rec.alt_model)
-                edges.extend(rec.edges)
-                bin_nums.append(len(rec.edges))
-            lengths.append(rec.length)
-            types += kind
-        self.recognizer_types = types
-        self.recognizers_flat = np.array(pssm_vals, dtype=np.dtype('d'))
-        self.recognizer_lengths = np.array(lengths, dtype=np.dtype('i'))
-        self.recognizer_models = np.array(models, dtype=np.dtype('d'))
-        self.recognizer_bin_nums = np.array(bin_nums, dtype=np.dtype('i'))
-        self.recognizer_bin_edges = np.array(edges, dtype=np.dtype('d'))
-        self.set_sum_recognizer_lengths()
-        con = []
-        if self.is_precomputed:
-            for c in self.connectors:
-                con += [c._mu, c._sigma]
-                con += (c.stored_pdfs + c.stored_cdfs)
-        else:
-            for c in self.connectors:
-                con += [c._mu, c._sigma]
-        self.connectors_scores_flat = np.array(con, dtype=np.dtype('d'))
+        flatten_organism(self)
 
     def count_recognizers(self) -> int:
         return len(self.recognizers)
