@@ -213,6 +213,9 @@ struct fl_ctx {
     DevBuf fb_item_count, fb_item_seqs, fb_unit_begin, fast_scratch, work_counter;
   } lanes[kLanes];
   cudaEvent_t ready = nullptr;
+  DevBuf single_arena;             // fl_calculate: device arena and pinned staging buffer of the one-placement path
+  void *single_stage = nullptr;
+  size_t single_stage_cap = 0;
   int fast_reg_warps[64] = {0};
   std::vector<double> h_den;  // host copy of DEN_EXPANSION (fits_int16)
   long long fast_pairs = 0, fallback_pairs = 0;  // statistics of the last fl_place_batch
@@ -316,6 +319,8 @@ extern "C" int fl_ctx_destroy(fl_ctx *ctx) {
     if (ln.stream && ln.stream != ctx->stream) cudaStreamDestroy(ln.stream);
   }
   if (ctx->ready) cudaEventDestroy(ctx->ready);
+  ctx->single_arena.release();
+  if (ctx->single_stage) cudaFreeHost(ctx->single_stage);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return FL_OK;
@@ -1231,49 +1236,158 @@ extern "C" int fl_calculate(fl_ctx *ctx, const char *sequence, int seq_len, cons
       ++shape_i;
     }
   }
-  const int rec_begin[2] = {0, n_rec};
-  const long long pool_begin[2] = {0, (long long)pool.size()};
-  const int con_M = n_rec > 1 ? M : 0;
-  fl_population pop;
-  pop.n_org = 1;
-  pop.n_rec_total = n_rec;
-  pop.rec_begin = rec_begin;
-  pop.rec_type = rec_types;
-  pop.rec_len = rec_lengths;
-  pop.rec_nb = rec_nb.data();
-  pop.rec_data = rec_data.data();
-  pop.pool_begin = pool_begin;
-  pop.rec_pool = pool.data();
-  pop.n_pool = (long long)pool.size();
-  pop.con_M = &con_M;
-  pop.con_pool = con_matrices;
-  pop.n_con = n_rec > 1 ? n_con_doubles : 0;
-  pop.rec_class = rec_class.data();
-  pop.n_classes = (int)cls_kind.size();
-  pop.cls_kind = cls_kind.data();
-  pop.cls_len = cls_len.data();
-  pop.cls_nb = cls_nb.data();
-  pop.cls_edges = cls_edges.data();
-  pop.edges_pool = edges_pool.data();
-  pop.n_edges = (long long)edges_pool.size();
-  int rc = upload_population(ctx, ctx->scratch_pop, &pop);
-  if (rc) return rc;
-  SeqSet &set = ctx->sets[FL_MAX_SETS];
-  const long long offs[2] = {0, seq_len};
-  if ((rc = upload_sequences(ctx, set, sequence, offs, 1))) return rc;
-  const long long con_begin = 0;
-  double energy = 0.0;
-  std::vector<int> gaps(n_rec);
-  std::vector<double> rsc(n_rec), csc(n_rec);
-  rc = place_batch(ctx, ctx->scratch_pop, set, &con_begin, FL_WANT_TRACE | FL_EXACT_ONLY,  // one pair: the exact kernel alone is the shortest path
-                    &energy, gaps.data(), rsc.data(), csc.data());
-  if (rc) return rc;
-  for (int i = 0; i < n_rec; ++i) {
-    rec_scores[i] = rsc[i];
-    con_lengths[i] = gaps[i];
-    if (i + 1 < n_rec) con_scores[i] = csc[i];
+  // ---- one placement = ONE upload, three small kernels, ONE download -------------------------------------------
+  // Everything the kernels read goes into one blob (pinned staging buffer -> device arena, a single copy): the
+  // one-organism population, the shape classes, the raw sequence; the arena also holds what pack_sequences_kernel and
+  // shape_bins_kernel produce and the result block.  The reference's callers make one such call per (organism,
+  // sequence) -- 100 + 100 per fitness evaluation -- so the ~35 separate copies of the batched entry points
+  // (fl_upload_population + fl_upload_sequences + fl_place_batch, 0.19 ms) are worth avoiding here.
+  int sum_len = 0;
+  for (int i = 0; i < n_rec; ++i) sum_len += rec_lengths[i];
+  if (sum_len > seq_len)
+    return fail(FL_E_TOO_LARGE, "organism 0 (sum of recognizer lengths %d) is too large to be placed on a sequence of length %d", sum_len, seq_len);
+  const int Pn = seq_len - sum_len + 1;
+  if (n_rec > 1) {
+    if (seq_len - sum_len > M - 1)
+      return fail(FL_E_UNSUPPORTED, "organism 0: gap tables cover %d lengths but a sequence of length %d needs %d (legacy non-precomputed branch, organism.c:336-338)",
+                  M, seq_len, seq_len - sum_len + 1);
+    if (seq_len - sum_len + n_rec > 10000)
+      return fail(FL_E_UNSUPPORTED, "effective length %d exceeds DEN_EXPANSION (10000 entries, _constants.h:11)", seq_len - sum_len + n_rec);
   }
-  rec_scores[n_rec] = energy;
+  const int n_cls = (int)cls_kind.size();
+  for (int c = 0; c < n_cls; ++c)
+    if (cls_nb[c] > 256) return fail(FL_E_UNSUPPORTED, "shape class %d has %d bin edges (supported: 2..256)", c, cls_nb[c]);
+  struct Blob {
+    std::vector<unsigned char> bytes;
+    size_t add(const void *src, size_t n, size_t align = 16) {
+      const size_t off = (bytes.size() + align - 1) / align * align;
+      bytes.resize(off + n, 0);
+      if (src && n) memcpy(bytes.data() + off, src, n);
+      return off;
+    }
+  } blob;
+  const int i_rec_begin[2] = {0, n_rec}, i_zero = 0, i_M = n_rec > 1 ? M : 0;
+  const long long l_pool_begin[2] = {0, (long long)pool.size()}, l_zero = 0, l_offs[2] = {0, seq_len};
+  const long long bins_row_stride = (seq_len + 15) & ~15LL;
+  const size_t o_result = blob.add(nullptr, 16 + 8 + (size_t)n_rec * (4 + 8 + 8) + 32);   // err flag | E | gaps | rsc | csc (zeroed)
+  const size_t o_rec_begin = blob.add(i_rec_begin, sizeof i_rec_begin), o_rec_len = blob.add(rec_lengths, (size_t)n_rec * 4);
+  const size_t o_rec_nb = blob.add(rec_nb.data(), (size_t)n_rec * 4), o_rec_class = blob.add(rec_class.data(), (size_t)n_rec * 4);
+  const size_t o_con_M = blob.add(&i_M, 4), o_sum_len = blob.add(&sum_len, 4), o_zero_i = blob.add(&i_zero, 4), o_seq_len = blob.add(&seq_len, 4);
+  const size_t o_cls_len = blob.add(cls_len.data(), (size_t)n_cls * 4), o_cls_nb = blob.add(cls_nb.data(), (size_t)n_cls * 4);
+  const size_t o_rec_type = blob.add(rec_types, (size_t)n_rec), o_cls_kind = blob.add(cls_kind.data(), (size_t)n_cls);
+  const size_t o_raw = blob.add(sequence, (size_t)seq_len);
+  blob.add(nullptr, 16);
+  const size_t o_rec_data = blob.add(rec_data.data(), (size_t)n_rec * 8), o_pool_begin = blob.add(l_pool_begin, sizeof l_pool_begin);
+  const size_t o_zero_l = blob.add(&l_zero, 8), o_offs = blob.add(l_offs, sizeof l_offs), o_cls_edges = blob.add(cls_edges.data(), (size_t)n_cls * 8);
+  const size_t o_pool = blob.add(pool.data(), pool.size() * 8), o_con = blob.add(n_rec > 1 ? con_matrices : nullptr, n_rec > 1 ? (size_t)n_con_doubles * 8 : 0);
+  const size_t o_edges = blob.add(edges_pool.data(), edges_pool.size() * 8);
+  const size_t upload_bytes = blob.add(nullptr, 16);
+  // device-only part of the arena
+  const size_t o_packed = blob.add(nullptr, ((size_t)(seq_len + 15) / 16 + 2) * 4), o_unk = blob.add(nullptr, ((size_t)(seq_len + 31) / 32 + 2) * 4);
+  const size_t o_has_unk = blob.add(nullptr, 16), o_k8 = blob.add(nullptr, (((size_t)seq_len + kK8Pad + 15) & ~(size_t)15) + 16);
+  const size_t o_bins = blob.add(nullptr, (size_t)std::max(1, n_cls) * (size_t)bins_row_stride + 16);
+  const size_t arena_bytes = blob.add(nullptr, 256);
+  int rc;
+  if ((rc = ctx->single_arena.ensure(arena_bytes))) return rc;
+  if (ctx->single_stage_cap < upload_bytes) {
+    if (ctx->single_stage) cudaFreeHost(ctx->single_stage);
+    ctx->single_stage = nullptr;
+    ctx->single_stage_cap = 0;
+    CK(cudaMallocHost(&ctx->single_stage, upload_bytes * 2 + 4096));
+    ctx->single_stage_cap = upload_bytes * 2 + 4096;
+  }
+  memcpy(ctx->single_stage, blob.bytes.data(), upload_bytes);
+  unsigned char *A = ctx->single_arena.as<unsigned char>();
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(A, ctx->single_stage, upload_bytes, cudaMemcpyHostToDevice, st));
+  auto at = [&](size_t off) { return A + off; };
+  pack_sequences_kernel<<<1, 64, 0, st>>>(at(o_raw), (const long long *)at(o_offs), (const int *)at(o_zero_i), (const int *)at(o_zero_i),
+                                        (unsigned *)at(o_packed), (unsigned *)at(o_unk), at(o_has_unk), (const int *)at(o_zero_i), at(o_k8));
+  if (n_cls > 0) {
+    ShapeBinParams q;
+    q.packed = (const unsigned *)at(o_packed);
+    q.word_off = (const int *)at(o_zero_i);
+    q.seq_len = (const int *)at(o_seq_len);
+    q.n_seq = 1;
+    q.cls_kind = (const char *)at(o_cls_kind);
+    q.cls_len = (const int *)at(o_cls_len);
+    q.cls_nb = (const int *)at(o_cls_nb);
+    q.cls_edges = (const long long *)at(o_cls_edges);
+    q.edges_pool = (const double *)at(o_edges);
+    q.tables = ctx->tables.as<double>();
+    q.bins = at(o_bins);
+    q.row_stride = bins_row_stride;
+    shape_bins_kernel<<<dim3(1u, (unsigned)n_cls), 128, 0, st>>>(q);
+  }
+  PlaceParams pp;
+  pp.rec_begin = (const int *)at(o_rec_begin);
+  pp.rec_type = (const char *)at(o_rec_type);
+  pp.rec_len = (const int *)at(o_rec_len);
+  pp.rec_nb = (const int *)at(o_rec_nb);
+  pp.rec_data = (const long long *)at(o_rec_data);
+  pp.pool_begin = (const long long *)at(o_pool_begin);
+  pp.rec_pool = (const double *)at(o_pool);
+  pp.con_M = (const int *)at(o_con_M);
+  pp.con_pool = (const double *)at(o_con);
+  pp.con_begin = (const long long *)at(o_zero_l);
+  pp.sum_len = (const int *)at(o_sum_len);
+  pp.org_list = (const int *)at(o_zero_i);
+  pp.packed = (const unsigned *)at(o_packed);
+  pp.unk = (const unsigned *)at(o_unk);
+  pp.word_off = (const int *)at(o_zero_i);
+  pp.k8g = at(o_k8);
+  pp.k8_off = (const int *)at(o_zero_i);
+  pp.unk_off = (const int *)at(o_zero_i);
+  pp.order = (const int *)at(o_zero_i);
+  pp.class_begin = 0;
+  pp.class_count = 1;
+  pp.S = seq_len;
+  pp.n_seq_total = 1;
+  pp.tables = ctx->tables.as<double>();
+  pp.rec_class = (const int *)at(o_rec_class);
+  pp.bins = at(o_bins);
+  pp.bins_row_stride = bins_row_stride;
+  // result block: [err flag, pad] [E] [rsc n] [csc n] [gaps n]
+  pp.err_flag = (int *)at(o_result);
+  pp.E = (double *)at(o_result + 16);
+  pp.rsc = pp.E + 1;
+  pp.csc = pp.rsc + n_rec;
+  pp.gaps = (int *)(pp.csc + n_rec);
+  pp.max_rec = n_rec;
+  pp.pool_stride = ((int)pool.size() + 1) & ~1;
+  pp.g_stride = (kGPad + Pn + kGPad + 1) & ~1;
+  pp.row_stride = (Pn + kMaxJ + 3) & ~3;
+  pp.code_stride = (seq_len + 15) & ~15;
+  pp.nrows = n_rec;
+  pp.seqs_per_cta = 1;
+  pp.chunks = 1;
+  int nwarps = 4;   // warps 1-3 only help with the prologue (gap tables); the pair itself is one warp's work
+  size_t smem = 0;
+  for (;; nwarps >>= 1) {
+    smem = 8ull * ((size_t)pp.pool_stride + (size_t)(n_rec - 1) * pp.g_stride + (size_t)nwarps * pp.nrows * pp.row_stride) +
+           sizeof(RecDesc) * n_rec + (size_t)nwarps * pp.code_stride;
+    if (smem <= (size_t)kMaxSmem || nwarps == 1) break;
+  }
+  if (smem > (size_t)kMaxSmem)
+    return fail(FL_E_UNSUPPORTED, "placement of %d offsets x %d recognizers needs %zu bytes of shared memory (limit %d)", Pn, n_rec, smem, kMaxSmem);
+  kPlaceKernels[pick_tile(Pn)][1]<<<1, nwarps * 32, smem, st>>>(pp);
+  CK(cudaGetLastError());
+  ctx->launches += n_cls > 0 ? 3 : 2;
+  const size_t result_bytes = 16 + 8 + (size_t)n_rec * (8 + 8 + 4);
+  unsigned char *host_result = (unsigned char *)ctx->single_stage + upload_bytes;   // second half of the pinned buffer
+  CK(cudaMemcpyAsync(host_result, at(o_result), result_bytes, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const int flag = *(const int *)host_result;
+  if (flag & ERR_NAN_NULL)
+    return fail(FL_E_NAN_NULL, "a shape score fell into a null-model bin whose frequency is NaN (the reference exits here, recognizer.c:258-262)");
+  const double *res = (const double *)(host_result + 16);
+  const int *res_gaps = (const int *)(res + 1 + 2 * n_rec);
+  for (int i = 0; i < n_rec; ++i) {
+    rec_scores[i] = res[1 + i];
+    con_lengths[i] = res_gaps[i];
+    if (i + 1 < n_rec) con_scores[i] = res[1 + n_rec + i];
+  }
+  rec_scores[n_rec] = res[0];
   return FL_OK;
 }
 
