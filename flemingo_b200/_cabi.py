@@ -23,7 +23,7 @@ EXPORTED = [
     "fl_upload_sequences", "fl_sequence_classes", "fl_upload_population", "fl_update_connectors", "fl_place_batch", "fl_fitness",
     "fl_fitness_dev",
     "fl_calculate", "fl_launch_count", "fl_path_stats", "fl_measure_dpx_rate",
-    "fl_build_connector_tables", "fl_round_decimals", "fl_build_shape_masses",
+    "fl_build_connector_tables", "fl_round_decimals", "fl_build_shape_masses", "fl_fitness_finalize",
 ]
 
 
@@ -81,6 +81,7 @@ def load_library() -> C.CDLL:
     lib.fl_build_connector_tables.argtypes = [vp, vp, ip, ip, dp, vp, vp, ip]
     lib.fl_round_decimals.argtypes = [vp, ll, ip]
     lib.fl_build_shape_masses.argtypes = [vp, vp, vp, vp, vp, ip, dp, vp, vp]
+    lib.fl_fitness_finalize.argtypes = [vp, ll]
     lib.fl_path_stats.argtypes = [vp, C.POINTER(ll), C.POINTER(ll), C.POINTER(ll)]
     lib.fl_launch_count.restype = ll
     lib.fl_launch_count.argtypes = [vp]

@@ -107,3 +107,13 @@ def shape_alt_models(mu, sigma, edges_list, pseudo_count: float) -> list:
         lo = int(begin[s]) - s
         out.append(log_mass[lo:lo + int(n_edges[s]) - 1] - log_auc[s])
     return out
+
+
+def fitness_finalize(stats: np.ndarray) -> np.ndarray:
+    """Recomputes column 0 of [n, 5] fitness statistics from M_pos, SE_pos, M_neg, SE_neg with the reference's own
+    arithmetic (fl_fitness_finalize); in place.  For rows that came off the device without passing through fl_fitness."""
+    lib = _cabi.load_library()
+    if not (stats.dtype == np.float64 and stats.flags.c_contiguous and stats.ndim == 2 and stats.shape[1] == 5):
+        raise ValueError("stats must be a C-contiguous float64 [n, 5] array")
+    _check(lib.fl_fitness_finalize(_ptr(stats), int(stats.shape[0])), "fl_fitness_finalize")
+    return stats

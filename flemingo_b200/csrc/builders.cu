@@ -117,3 +117,17 @@ extern "C" int fl_build_shape_masses(const double *mu, const double *sigma, cons
   });
   return FL_OK;
 }
+
+extern "C" int fl_fitness_finalize(double *stats, long long n_org) {
+  if (n_org < 0 || (n_org > 0 && !stats)) return FL_E_ARG;
+  // organism_object.py:954-956 with numpy scalars: `**` is libm pow(), also for the squares.  The exponents are read
+  // through volatiles so that the compiler cannot fold pow(x, 2.0) into x * x or pow(x, 0.5) into sqrt(x): libm's pow is
+  // accurate to ~0.52 ulp, not correctly rounded, and the reference gets whatever it returns.
+  volatile double two_v = 2.0, half_v = 1.0 / 2.0;
+  const double two = two_v, half = half_v;
+  for (long long o = 0; o < n_org; ++o) {
+    double *r = stats + 5 * o;
+    r[0] = (r[1] - r[3]) / std::pow(std::pow(r[2], two) + std::pow(r[4], two), half);
+  }
+  return FL_OK;
+}

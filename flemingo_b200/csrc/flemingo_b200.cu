@@ -1156,6 +1156,8 @@ static int fitness_launch(fl_ctx *ctx, int pos_set, int neg_set, int method, dou
   if (rows > n_org) CK(cudaMemsetAsync(ctx->fit_out.as<double>() + (size_t)n_org * 5, 0, (size_t)(rows - n_org) * 5 * 8, ctx->stream));
   if (n_org == 0) return FL_OK;
   if (sp.n_seq < 1 || sn.n_seq < 1) return fail(FL_E_ARG, "fl_fitness: empty sequence set");
+  if (std::max(sp.n_seq, sn.n_seq) > 60 * kPwLeafCap)
+    return fail(FL_E_UNSUPPORTED, "fl_fitness: sets of more than %d sequences exceed the reduction plan of the fitness kernel", 60 * kPwLeafCap);
   // n_to_trim = round(gamma * N): python rounds half to even (organism_object.py:892), as nearbyint does
   const int trim_p = (int)std::nearbyint(gamma * (double)sp.n_seq);
   const int trim_n = (int)std::nearbyint(gamma * (double)sn.n_seq);
@@ -1177,7 +1179,9 @@ extern "C" int fl_fitness(fl_ctx *ctx, int pos_set, int neg_set, int method, dou
   if (rc) return rc;
   if (n_org == 0) return FL_OK;
   CK(cudaMemcpyAsync(out, ctx->fit_out.p, (size_t)n_org * 5 * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  return check_device_errors(ctx);
+  const int rc2 = check_device_errors(ctx);   // synchronises
+  if (rc2) return rc2;
+  return fl_fitness_finalize(out, n_org);
 }
 
 extern "C" int fl_fitness_dev(fl_ctx *ctx, int pos_set, int neg_set, int method, double gamma, int pad_rows, void **out_dev) {

@@ -10,6 +10,8 @@ from __future__ import annotations
 
 import numpy as np
 
+from .builders import fitness_finalize
+
 
 def shard_by_cost(costs, world_size: int) -> list:
     """Largest-processing-time-first greedy partition; returns world_size index arrays (each ascending).
@@ -114,7 +116,7 @@ class DeviceGather:
         self.engine.sync()          # surfaces device-side errors (NaN null bin) like fl_fitness does
         full = np.empty((self.n_org, 5))
         full[self._orgs] = self.host.numpy()[self._rows]
-        return full
+        return fitness_finalize(full)     # column 0 with the reference's host arithmetic, as fl_fitness does
 
 
 class MultiDeviceEvaluator:

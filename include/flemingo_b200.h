@@ -154,6 +154,15 @@ int fl_fitness(fl_ctx *ctx, int pos_set, int neg_set, int method, double gamma, 
 int fl_fitness_dev(fl_ctx *ctx, int pos_set, int neg_set, int method, double gamma, int pad_rows, void **out_dev);
 
 /*
+ * Host code: recomputes column 0 of n_org rows [fitness, M_pos, SE_pos, M_neg, SE_neg] from the other four exactly as
+ * OrganismObject.set_fitness does (organism_object.py:954-956: `(M_p - M_n) / (SE_p ** 2 + SE_n ** 2) ** (1/2)` on numpy
+ * scalars, i.e. with libm pow()).  fl_fitness applies it before returning; callers that take the statistics from
+ * fl_fitness_dev (the multi-GPU gather) apply it to the gathered rows.  M and SE come off the device bit-identical to
+ * numpy's np.mean / np.std (pairwise summation order, csrc/fitness_kernel.cuh).
+ */
+int fl_fitness_finalize(double *stats, long long n_org);
+
+/*
  * One placement with the exact argument list of _multiplacement.calculate (src/_interface.c:45-185,
  * kwlist :49-52): sequence (+length), rec_types (+n_rec), rec_matrices, rec_lengths, con_matrices,
  * rec_scores (out, n+1), con_scores (out, n-1), con_lengths (out, n), max_length, bin_freqs, bin_edges,

@@ -141,3 +141,56 @@ def test_builders_match_the_reference_classes(golden_null_models):
             ref = ShapeObject(kind, L, conf["shape"], mu, sigma)
             got = builders.shape_alt_models([ref._mu], [ref._sigma], [ref.edges], ref.pseudo_count)[0]
             assert np.array(ref.alt_model).tobytes() == got.tobytes()
+
+
+def test_flatten_on_array_twins_equals_flatten_on_lists(golden_null_models):
+    """flatten_organism concatenates the array twins the builders leave next to every table; an organism whose tables
+    are plain lists (built elsewhere) goes through the conversion path.  Both give the same flat arrays, and a deep copy
+    -- the reference's clone_organism -- keeps tables, twins and their identity."""
+    import copy
+
+    from flemingo_b200 import builders, synthetic
+    from flemingo_b200.flatten import flatten_organism
+    orgs = synthetic.mixed_organisms(30, 200, 17) + synthetic.pssm_organisms(5, 200, 18)
+    names = ("recognizers_flat", "recognizer_lengths", "recognizer_models", "recognizer_bin_edges", "recognizer_bin_nums",
+             "connectors_scores_flat")
+    for org in orgs:
+        want = {k: getattr(org, k).copy() for k in names}
+        clone = copy.deepcopy(org)
+        for con in clone.connectors:
+            assert isinstance(con.stored_pdfs, builders.TableList) and con.stored_pdfs.np is not None
+            assert con.stored_pdfs == list(con.stored_pdfs.np)
+        # strip every twin: plain lists, no cached PSSM rows
+        for con in clone.connectors:
+            con.stored_pdfs, con.stored_cdfs = list(con.stored_pdfs), list(con.stored_cdfs)
+        for rec in clone.recognizers:
+            if rec.get_type() == 'p':
+                rec._pssm_flat = None
+            else:
+                rec.alt_model = list(rec.alt_model)
+        flatten_organism(clone)
+        for k in names:
+            got = getattr(clone, k)
+            assert got.dtype == want[k].dtype and got.tobytes() == want[k].tobytes(), k
+        assert clone.recognizer_types == org.recognizer_types and clone.sum_recognizer_lengths == org.sum_recognizer_lengths
+    # a PSSM twin is only trusted while `pssm` is the array it was derived from
+    org = synthetic.pssm_organisms(1, 100, 19)[0]
+    rec = org.recognizers[0]
+    rec.pssm = np.array([dict(col, a=col["a"] + 1.0) for col in rec.pssm])
+    org.flatten()
+    assert org.recognizers_flat[0] == rec.pssm[0]["a"]
+
+
+def test_fitness_finalize_is_the_reference_expression_on_numpy_scalars():
+    """fl_fitness_finalize recomputes (M_p - M_n) / (SE_p ** 2 + SE_n ** 2) ** (1/2) as OrganismObject.set_fitness does
+    with numpy scalars (organism_object.py:954-956) -- bit for bit."""
+    rng = np.random.default_rng(12)
+    stats = np.empty((20000, 5))
+    stats[:, 1] = rng.normal(-20, 15, 20000)
+    stats[:, 3] = rng.normal(-25, 15, 20000)
+    stats[:, 2] = np.maximum(1.0, rng.gamma(2.0, 2.0, 20000)) / np.sqrt(rng.integers(1, 20000, 20000))
+    stats[:, 4] = np.maximum(1.0, rng.gamma(2.0, 2.0, 20000)) / np.sqrt(rng.integers(1, 20000, 20000))
+    stats[:, 0] = 0.0
+    want = np.array([(np.float64(r[1]) - np.float64(r[3])) / (np.float64(r[2]) ** 2 + np.float64(r[4]) ** 2) ** (1 / 2) for r in stats])
+    got = builders.fitness_finalize(stats.copy())[:, 0]
+    assert got.tobytes() == want.tobytes()

@@ -1,9 +1,10 @@
 """GPU parity tests: the CUDA path, called through the C ABI, against (a) the committed golden fixtures that
 the reference itself produced and (b) the CPU oracle on seeded synthetic inputs.
 
-Bar: energies, node scores and placement offsets BIT-EXACT (==).  The kernels do all arithmetic in IEEE
-double in the reference's operand order, so no tolerance is needed; fitness statistics are compared at
-rtol 1e-9 (summation order of the device reduction differs from numpy's pairwise sum; north_star allows 1e-5).
+Bar: energies, node scores, placement offsets AND fitness statistics BIT-EXACT (==).  The kernels do all arithmetic in
+IEEE double in the reference's operand order; the fitness reduction follows numpy's pairwise summation order and the
+final quotient is formed on the host with the same libm calls the reference's numpy scalars make, so no tolerance is
+needed anywhere (north_star allows 1e-5).
 """
 import numpy as np
 import pytest
@@ -13,7 +14,12 @@ from tests.helpers import assert_placement_equals_golden
 
 pytestmark = pytest.mark.gpu
 
-FIT_RTOL = 1e-9
+
+
+def same_doubles(got, want):
+    """bit-identical float64 arrays (NaNs in the same places)"""
+    return np.array_equal(np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64), equal_nan=True)
+
 
 
 def test_golden_cases_batched_trace(engine, golden_cases):
@@ -84,7 +90,7 @@ def test_golden_fitness_all_methods(engine, golden_cases):
         for f in case["fitness"]:
             got = engine.fitness(sp, sn, f["method"], f["gamma"])[0]
             want = np.array([f["fitness"], f["M_p"], f["SE_p"], f["M_n"], f["SE_n"]])
-            assert np.allclose(got, want, rtol=FIT_RTOL, atol=0, equal_nan=True), (case["name"], f, got)
+            assert same_doubles(got, want), (case["name"], f, got, want)
             n += 1
     assert n > 300
 
@@ -98,9 +104,9 @@ def test_object_api_matches_golden_fitness(engine, golden_cases):
     assert energies == [p["energy"] for p in case["placements"]]
     for f in case["fitness"]:
         org.set_fitness(pos, neg, f["method"], f["gamma"])
-        assert np.isclose(org.fitness, f["fitness"], rtol=FIT_RTOL, equal_nan=True)
+        assert same_doubles(org.fitness, f["fitness"])
         m, se = org.get_M_and_SE_on_DNA_set(pos, f["method"], f["gamma"])
-        assert np.isclose(m, f["M_p"], rtol=FIT_RTOL, equal_nan=True) and np.isclose(se, f["SE_p"], rtol=FIT_RTOL)
+        assert same_doubles(m, f["M_p"]) and same_doubles(se, f["SE_p"])
     with pytest.raises(ValueError):
         org.set_fitness(pos, neg, "NoSuchMethod", 0.2)
 
@@ -379,7 +385,7 @@ def test_full_size_config3_vs_oracle(engine):
     stats = engine.fitness(sp, sn, "Welch", 0.2)
     for o in range(0, 2000, 97):
         want = oracle.fitness_stats(res.energies[o, :5000], res.energies[o, 5000:], "Welch", 0.2)
-        assert np.allclose(stats[o], want, rtol=FIT_RTOL)
+        assert same_doubles(stats[o], want)
 
 
 def test_full_size_config4_vs_oracle(engine):
@@ -415,7 +421,7 @@ def test_full_size_config5_generation_vs_oracle(engine):
     stats = engine.fitness(sp, sn, "Welch", 0.2)
     en = engine.place(sn).energies
     for o in range(0, 4096, 211):
-        assert np.allclose(stats[o], oracle.fitness_stats(ep[o], en[o], "Welch", 0.2), rtol=FIT_RTOL)
+        assert same_doubles(stats[o], oracle.fitness_stats(ep[o], en[o], "Welch", 0.2))
 
 
 def test_minus_infinity_pssm_entries(engine):
