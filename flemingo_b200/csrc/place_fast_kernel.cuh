@@ -1104,6 +1104,7 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
 
   // rounds are claimed dynamically: a warp that met a pair with several candidates (a longer refinement) takes fewer
   // rounds, and the warps of the CTA drift apart instead of marching through the phases in lockstep
+  // (static assignment -- warp w takes rounds w, w + nwarps, ... -- measures the same: 162.3 vs 162.8 ms on config 3)
   for (;;) {
     int round = 0;
     if (lane == 0) round = atomicAdd(&sm.plan->next_round, 1);

@@ -131,7 +131,11 @@ class MultiDeviceEvaluator:
         stats = evaluator(organisms, pos, neg, "Welch", 0.2)      # [n_org, 5], same doubles as a single engine
     """
 
-    def __init__(self, devices=None):
+    def __init__(self, devices=None, engines=None):
+        """devices: CUDA device indices (default: all visible); engines: ready-made engines instead (tests)."""
+        if engines is not None:
+            self.engines = list(engines)
+            return
         from . import _cabi
         from .engine import Engine
         if devices is None:

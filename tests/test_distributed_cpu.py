@@ -63,3 +63,48 @@ def test_two_rank_gloo_gathers_whole_population():
 def test_gather_stats_single_rank_identity():
     stats = np.arange(15.0).reshape(3, 5)
     assert np.array_equal(gather_stats(stats, [np.arange(3)], 0, 1), stats)
+
+
+class RecordingEngine:
+    """Stand-in for one device of MultiDeviceEvaluator: records the call order, answers like FakeEngine."""
+
+    def __init__(self, name, log):
+        self.name, self.log, self.orgs, self.sets = name, log, None, {}
+
+    @staticmethod
+    def join_sequences(seqs):
+        return "".join(seqs).encode(), np.array([len(s) for s in seqs])
+
+    def upload_sequences(self, seqs, set_id, reuse=False, joined=None):
+        assert joined is not None and reuse          # joined once by the evaluator, resident across generations
+        self.sets[set_id] = list(seqs)
+        return set_id
+
+    def upload_population(self, organisms):
+        self.orgs = list(organisms)
+        self.log.append((self.name, "upload", len(self.orgs)))
+
+    def place(self, sset, fetch=True):
+        assert fetch is False                        # asynchronous: nothing is read back before every device is busy
+        self.log.append((self.name, "place", sset))
+
+    def fitness(self, pos, neg, method, gamma):
+        self.log.append((self.name, "fitness"))
+        return FakeEngine().evaluate(self.orgs, self.sets[pos], self.sets[neg], method, gamma)
+
+
+def test_multi_device_evaluator_issues_everything_before_collecting():
+    from flemingo_b200.distributed import MultiDeviceEvaluator
+    log = []
+    ev = MultiDeviceEvaluator(engines=[RecordingEngine(f"gpu{d}", log) for d in range(3)])
+    orgs = [Org(1 + i % 6, 5 + (7 * i) % 40) for i in range(41)]
+    pos, neg = ["a" * 100] * 3, ["c" * 100] * 4
+    got = ev(orgs, pos, neg, "Welch", 0.2)
+    assert np.array_equal(got, FakeEngine().evaluate(orgs, pos, neg, "Welch", 0.2))
+    first_fitness = next(i for i, e in enumerate(log) if e[1] == "fitness")
+    assert all(e[1] != "fitness" for e in log[:first_fitness]) and all(e[1] == "fitness" for e in log[first_fitness:])
+    assert sorted(e[2] for e in log if e[1] == "upload") and sum(e[2] for e in log if e[1] == "upload") == 41
+    # fewer organisms than devices: idle devices are skipped
+    log.clear()
+    assert np.array_equal(ev(orgs[:2], pos, neg), FakeEngine().evaluate(orgs[:2], pos, neg, "Welch", 0.2))
+    assert len([e for e in log if e[1] == "upload"]) == 2
