@@ -1,12 +1,14 @@
-// place_fast_kernel.cuh -- filter-and-refine placement: an int32 fixed-point DPX pass finds, with a rigorous
-// error bound, every DP cell that can lie on the optimal path; those few cells are then re-evaluated in exact
-// IEEE double in the reference's operand order.  Results are bit-identical to the reference; pairs for which
-// the candidate sets grow too large (massive ties) or that the fixed-point range cannot hold are pushed to a
-// device-side list and placed by the exact kernel (place_list_kernel).
+// place_fast_kernel.cuh -- filter-and-refine placement: an integer fixed-point DPX pass (int32, or packed 16-bit:
+// two DP cells per instruction) finds, with a rigorous error bound, every DP cell that can lie on the optimal path;
+// those few cells are then re-evaluated in exact IEEE double in the reference's operand order.  Results are
+// bit-identical to the reference; pairs for which the candidate sets grow too large (massive ties) or that the
+// fixed-point range cannot hold are filed in device-side lists -- from the packed pass for a second chance on the int32
+// pass, from the int32 pass for the exact kernel (place_list_kernel).
 //
 // Why it is exact.  Let C be the reference's doubles (organism.c:347-369), Chat the same sums in real
 // arithmetic (|C - Chat| < 2^-30 units after scaling, see `slack`), and Cq the integer pass with every table
-// entry rounded to the nearest integer in units of 1/s (s a power of two, so scaling itself is exact):
+// entry rounded to the nearest integer in units of 1/s (s a power of two, so scaling itself is exact; the packed pass
+// may also use 100 * 2^e, under which 2-decimal PSSM entries are integers up to ~1e-13 units, covered by the slack):
 //     |Cq_i[j] - s*Chat_i[j]| <= err_i = 0.5 * (number of rounded table entries on a path up to stage i).
 // Therefore every j that maximises C_{n-1} has Cq_{n-1}[j] >= max Cq_{n-1} - 2 err_{n-1} - slack, and every k
 // that can win cell (i, j) has Cq_{i-1}[k] + Gq[j-k] >= (Cq_i[j] - Rq_i[j]) - 2 (err_{i-1} + 0.5) - slack.
@@ -71,8 +73,8 @@ struct FastParams {
   const int *retry_seqs;
   unsigned long long *retried_total;  // statistics: pairs that took the second chance
   int gq_stride;     // ints per quantised connector table (kGPad + Pmax + kGPad)
-  int rowq_stride;   // ints per quantised row
-  int slotq_stride;  // ints per pair slot (1 or 2 rows), == TEAM (mod 32) so that teams hit disjoint banks
+  int rowq_stride;   // row ELEMENTS (int32 or int16) per quantised row
+  int slotq_stride;  // row elements per pair slot (1 or 2 rows); in 32-bit words == TEAM (mod 32): teams hit disjoint banks
   int single_row;    // 1: ONE quantised row per pair in shared memory -- the DP stage runs in place (dp_stage) and every
                      // older row is streamed back from global scratch when the refinement needs it; chosen by the host
                      // when halving the row storage lets more warps (a higher multiple of four) live on an SM
@@ -81,7 +83,7 @@ struct FastParams {
   int kmer_cap;      // ints available for the 4-mer tables of one organism
   int want_trace;
   int *scratch;      // global rows 0..n-3 of every resident pair slot (only the last two rows stay in shared memory)
-  long long scratch_slot_stride;  // ints per pair slot in `scratch` (max_rec * rowq_stride)
+  long long scratch_slot_stride;  // row elements per pair slot in `scratch` (max_rec * rowq_stride)
   int *work_counter;  // device counter the persistent CTAs claim work items from (zeroed before the launch)
   int n_items;        // organisms of the bucket x chunks
 };
