@@ -84,17 +84,22 @@ static int pick_tile(int P) {
 // organisms whose whole value range fits int16 at a useful scale (place_fast_kernel.cuh); J = 2 * odd there (bank layout).
 typedef void (*fast_kernel_fn)(const FastParams);
 struct FastConfig {
-  int J, team, bits;
+  int J, team, bits, prune;
   fast_kernel_fn fn;
 };
-#define FAST_CFG(J, T) {J, T, 32, place_fast_kernel<J, T, 32>}
-#define FAST_CFG16(J, T) {J, T, 16, place_fast_kernel<J, T, 16>}
+#define FAST_CFG(J, T) {J, T, 32, 0, place_fast_kernel<J, T, 32>}
+#define FAST_CFG16(J, T) {J, T, 16, 0, place_fast_kernel<J, T, 16>}
+// kernels with pruned stages (dp_stage_pruned) for organisms whose connectors are tight: small tiles, so that the tiles
+// around the peak of the gap energies are few cells; one configuration per range of P (4 rounds of TEAM row blocks)
+#define FAST_CFGP(J, T) {J, T, 32, 1, place_fast_kernel<J, T, 32, true>}
+#define FAST_CFGP16(J, T) {J, T, 16, 1, place_fast_kernel<J, T, 16, true>}
 static const FastConfig kFastConfigs[] = {
     FAST_CFG(3, 8),  FAST_CFG(5, 8),  FAST_CFG(7, 8),  FAST_CFG(9, 8),  FAST_CFG(11, 8), FAST_CFG(13, 8), FAST_CFG(15, 8),
     FAST_CFG(17, 8), FAST_CFG(19, 8), FAST_CFG(21, 8), FAST_CFG(9, 16), FAST_CFG(11, 16), FAST_CFG(13, 16), FAST_CFG(15, 16), FAST_CFG(17, 16), FAST_CFG(19, 16),
     FAST_CFG(21, 16), FAST_CFG(13, 32), FAST_CFG(17, 32), FAST_CFG(21, 32),
     FAST_CFG16(6, 8), FAST_CFG16(10, 8), FAST_CFG16(14, 8), FAST_CFG16(18, 8), FAST_CFG16(22, 8), FAST_CFG16(10, 16), FAST_CFG16(14, 16),
-    FAST_CFG16(18, 16), FAST_CFG16(22, 16), FAST_CFG16(14, 32), FAST_CFG16(18, 32), FAST_CFG16(22, 32)};
+    FAST_CFG16(18, 16), FAST_CFG16(22, 16), FAST_CFG16(14, 32), FAST_CFG16(18, 32), FAST_CFG16(22, 32),
+    FAST_CFGP(9, 8), FAST_CFGP(13, 16), FAST_CFGP(17, 32), FAST_CFGP16(10, 8), FAST_CFGP16(14, 16), FAST_CFGP16(18, 32)};
 constexpr int kNumFastConfigs = (int)(sizeof(kFastConfigs) / sizeof(kFastConfigs[0]));
 
 // Estimated issue slots per pair: tiles x (cells + loads and bookkeeping), scaled by the share of the warp a team uses.
@@ -110,23 +115,31 @@ static double fast_cost(int P, int J, int team, int bits) {
   }
   return slots * team / 32.0;
 }
-static int pick_fast(int P, int bits) {
+static int pick_fast(int P, int bits, int prune = 0) {
   int best = -1;
   double best_cost = 1e300;
+  if (prune) {  // the first configuration whose four rounds of TEAM row blocks cover P (the list is sorted by TEAM)
+    for (int i = 0; i < kNumFastConfigs; ++i)
+      if (kFastConfigs[i].prune && kFastConfigs[i].bits == bits) {
+        best = i;
+        if (4 * kFastConfigs[i].team * kFastConfigs[i].J >= P) break;
+      }
+    return best;
+  }
   // experiments: FLEMINGO_FAST_CFG="J,TEAM" forces one configuration (of the arithmetic that has it)
   static const char *force = getenv("FLEMINGO_FAST_CFG");
   if (force) {
     int fj = 0, ft = 0;
     if (sscanf(force, "%d,%d", &fj, &ft) == 2)
       for (int i = 0; i < kNumFastConfigs; ++i)
-        if (kFastConfigs[i].J == fj && kFastConfigs[i].team == ft && kFastConfigs[i].bits == bits) return i;
+        if (kFastConfigs[i].J == fj && kFastConfigs[i].team == ft && kFastConfigs[i].bits == bits && !kFastConfigs[i].prune) return i;
   }
   // the choice depends on (P, bits) only: a ragged dataset asks for every organism of every length class
   static std::vector<int> cache[2];
   std::vector<int> &memo = cache[bits == 16 ? 1 : 0];
   if (P >= 0 && P < (int)memo.size() && memo[P] >= 0) return memo[P];
   for (int i = 0; i < kNumFastConfigs; ++i) {
-    if (kFastConfigs[i].bits != bits) continue;
+    if (kFastConfigs[i].bits != bits || kFastConfigs[i].prune) continue;
     const double c = fast_cost(P, kFastConfigs[i].J, kFastConfigs[i].team, bits);
     if (c < best_cost) {
       best_cost = c;
@@ -194,6 +207,10 @@ struct Population {
   std::vector<double> rec_range;
   std::vector<int> n_units;    // rounded tables per organism (4-mer groups + shape recognizers): error budget
   std::vector<char> pssm_only; // every recognizer of the organism is a PSSM
+  // routing to the kernels with pruned stages: sigma of connector c of organism o at [rec_begin[o] + c], read from the
+  // block headers at the canonical pool layout (base tables in organism order, con_base_guess[o]); NaN if unknown
+  std::vector<float> con_sigma;
+  std::vector<long long> con_base_guess;
   long long n_con = 0;
   int max_pool = 0, min_sum_len = 0;
   DevBuf d_rec_begin, d_rec_type, d_rec_len, d_rec_nb, d_rec_data, d_pool_begin, d_rec_pool, d_con_M, d_con_pool, d_sum_len, d_rec_class, d_cls_kind, d_cls_len, d_cls_nb, d_cls_edges, d_edges_pool;
@@ -455,6 +472,9 @@ static int upload_population(fl_ctx *ctx, Population &P, const fl_population *po
   P.rec_range.assign((size_t)pop->n_rec_total, 0.0);
   P.n_units.assign(n_org, 0);
   P.pssm_only.assign(n_org, 1);
+  P.con_sigma.assign((size_t)pop->n_rec_total, NAN);
+  P.con_base_guess.assign(n_org, -1);
+  long long canon = 0;
   P.max_rec = 0;
   P.max_pool = 0;
   P.min_sum_len = 0x7fffffff;
@@ -479,6 +499,14 @@ static int upload_population(fl_ctx *ctx, Population &P, const fl_population *po
     }
     P.sum_len[o] = sl;
     P.pool_len[o] = (int)(pop->pool_begin[o + 1] - pop->pool_begin[o]);
+    if (n > 1 && P.con_M[o] >= 1) {
+      const long long stride = 2LL * P.con_M[o] + 2;
+      if (pop->con_pool && canon + (n - 1) * stride <= pop->n_con) {
+        P.con_base_guess[o] = canon;
+        for (int c = 0; c < n - 1; ++c) P.con_sigma[rb + c] = (float)pop->con_pool[canon + c * stride + 1];
+      }
+      canon += (n - 1) * stride;
+    }
     {
       // ints the integer fast path needs for this organism: 4-mer tables per PSSM, one bin table per shape recognizer
       int need = 0, units = 0;
@@ -659,6 +687,39 @@ static bool fits_int16(fl_ctx *ctx, const Population &P, int o, int S, std::map<
   return need == need && need > 0.0 && budget / need >= 32.0;
 }
 
+// Which organisms take a kernel with pruned stages (dp_stage_pruned): those whose estimated stage costs there -- a tight
+// connector's stage pruned, the others in full at the pruned kernel's smaller tile -- stay below 0.9 of the full stages
+// of the regular configuration.  The estimate uses sigma only (a Gaussian is within `drop` bits of its peak for
+// |g - mu| <= sigma sqrt(2 ln2 drop)) and fast_cost's unit, issue slots per pair; the kernel decides stage by stage from
+// the real tables, so a wrong guess costs time, never correctness.  mode: 0 never, 1 by estimate, 2 every organism (tests).
+static bool wants_prune(const Population &P, int o, int Po, int bits, long long cb, int mode, int drop, int frac) {
+  if (mode == 0) return false;
+  const int rb = P.rec_begin[o], n = P.rec_begin[o + 1] - rb;
+  if (n < 2) return false;
+  const int j = pick_fast(Po, bits, 1), j0 = pick_fast(Po, bits, 0);
+  if (j < 0 || j0 < 0) return false;
+  if (mode == 2) return true;
+  if (P.con_base_guess[o] < 0 || cb != P.con_base_guess[o]) return false;   // not the tables whose headers were read
+  const int J = kFastConfigs[j].J, team = kFastConfigs[j].team, NB = (Po + J - 1) / J;
+  const double tile = bits == 16 ? J * J / 2.0 + 2.5 * J + 24.0 : J * J + 3.0 * J + 24.0;
+  const double full_here = fast_cost(Po, J, team, bits);
+  const double full_regular = fast_cost(Po, kFastConfigs[j0].J, kFastConfigs[j0].team, bits);
+  const int rounds = (NB + team - 1) / team;
+  double cost = 0.0;
+  for (int c = 0; c < n - 1; ++c) {
+    const double sigma = P.con_sigma[rb + c];
+    double stage = full_here;
+    if (sigma >= 0.0) {
+      const double width = 2.0 * sigma * std::sqrt(1.3863 * drop) + 1.0;
+      const int tiles = (int)(width / J) + 2;
+      if ((long long)(tiles + 2) * frac <= NB)
+        stage = std::min(stage, rounds * (tiles * tile + 150.0 + 2.0 * J) * team / 32.0);
+    }
+    cost += stage;
+  }
+  return cost <= 0.9 * (n - 1) * full_regular;
+}
+
 static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long *con_begin, int flags, double *energies,
                        int *gaps, double *rec_scores, double *con_scores) {
   if (!P.valid) return fail(FL_E_STATE, "fl_place_batch: no population uploaded");
@@ -740,6 +801,12 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
   }
 
   const char *env_bits = getenv("FLEMINGO_FAST_BITS");   // experiments / tests: force one arithmetic (read at every call)
+  // pruned stages: FLEMINGO_PRUNE = 0 (never) / 1 (organisms with tight connectors, the default) / 2 (every organism);
+  // FLEMINGO_PRUNE_DROP, FLEMINGO_PRUNE_FRAC: see FastParams
+  const char *env_prune = getenv("FLEMINGO_PRUNE");
+  const int prune_mode = env_prune ? atoi(env_prune) : 1;
+  const int prune_drop = getenv("FLEMINGO_PRUNE_DROP") ? std::max(1, atoi(getenv("FLEMINGO_PRUNE_DROP"))) : 8;
+  const int prune_frac = getenv("FLEMINGO_PRUNE_FRAC") ? std::max(1, atoi(getenv("FLEMINGO_PRUNE_FRAC"))) : 3;
   // several length classes: their launch chains are independent and go round-robin onto the lanes
   const int n_lanes = n_cls > 1 ? fl_ctx::kLanes : 1;
   if (n_lanes > 1) {
@@ -804,7 +871,10 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
     // ---- buckets: integer fast path (PSSM-only organisms, P >= 2) by (J, TEAM); everything else exact by J ----
     const bool allow_fast = !(flags & FL_EXACT_ONLY);
     FastParams fp;
-    fp.gq_stride = kGPad + Pmax + kGPad;
+    fp.gq_stride = kGPad + Pmax + kGPad;   // per configuration below (the pruned kernels append their tile bounds)
+    fp.gt_off = fp.nb_max = fp.bm_stride = 0;
+    fp.prune_drop = prune_drop;
+    fp.prune_frac = prune_frac;
     fp.k8_stride = (cl.len + kK8Pad + 15) & ~15;  // the sequence's block of 4-mer codes, as laid out by pack_sequences_kernel
     fp.want_trace = trace ? 1 : 0;
     fp.has_unk = set.has_unk.as<unsigned char>();
@@ -815,17 +885,45 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
     for (int o = 0; o < n_org; ++o) {
       const int Po = cl.len - P.sum_len[o] + 1;
       if (allow_fast && P.kmer_need[o] > 0 && P.kmer_need[o] <= 16384 && Po >= 2) {
-        fast_bucket[pick_fast(Po, fits_int16(ctx, P, o, cl.len, den_cache, env_bits) ? 16 : 32)].push_back(o);
+        const int bits = fits_int16(ctx, P, o, cl.len, den_cache, env_bits) ? 16 : 32;
+        const int prune = wants_prune(P, o, Po, bits, con_begin[(size_t)c * n_org + o], prune_mode, prune_drop, prune_frac) ? 1 : 0;
+        fast_bucket[pick_fast(Po, bits, prune)].push_back(o);
         kmer_cap = std::max(kmer_cap, P.kmer_need[o]);
         ++n_fast_org;
       } else {
         exact_bucket[pick_tile(Po)].push_back(o);
       }
     }
+    // Splitting a length class's organisms of one arithmetic over a regular and a pruned launch pays only when both are
+    // large enough to fill the machine a few times over; otherwise the launch tails cost more than the pruned stages
+    // save and the smaller bucket joins the larger one (the pruned kernels run any organism: they decide per stage).
+    if (prune_mode == 1) {
+      const long long min_items = 4LL * n_sm;
+      auto items_of = [&](int j) { return (long long)fast_bucket[j].size() * ((cl.count + 255) / 256); };
+      for (int j = 0; j < kNumFastConfigs; ++j) {
+        if (!kFastConfigs[j].prune || fast_bucket[j].empty()) continue;
+        // the regular buckets of this arithmetic (one per (J, TEAM) picked for the organisms' P)
+        long long regular = 0;
+        for (int k = 0; k < kNumFastConfigs; ++k)
+          if (!kFastConfigs[k].prune && kFastConfigs[k].bits == kFastConfigs[j].bits) regular += items_of(k);
+        if (regular == 0) continue;
+        if (items_of(j) < min_items && items_of(j) <= regular) {
+          for (int o : fast_bucket[j]) fast_bucket[pick_fast(cl.len - P.sum_len[o] + 1, kFastConfigs[j].bits, 0)].push_back(o);
+          fast_bucket[j].clear();
+        } else if (regular < min_items) {
+          for (int k = 0; k < kNumFastConfigs; ++k) {
+            if (kFastConfigs[k].prune || kFastConfigs[k].bits != kFastConfigs[j].bits) continue;
+            for (int o : fast_bucket[k]) fast_bucket[pick_fast(cl.len - P.sum_len[o] + 1, kFastConfigs[k].bits, 1)].push_back(o);
+            fast_bucket[k].clear();
+          }
+        }
+      }
+    }
     fp.kmer_cap = kmer_cap;
     // fast-path geometry: warps per CTA chosen for the most resident warps per SM; if even one warp does not fit,
     // those organisms go to the exact kernel
     int fast_warps[kNumFastConfigs], fast_rowq[kNumFastConfigs], fast_slot[kNumFastConfigs], fast_ctas_per_sm[kNumFastConfigs];
+    int fast_gq[kNumFastConfigs], fast_nb[kNumFastConfigs], fast_bm[kNumFastConfigs];
     bool fast_single[kNumFastConfigs] = {false}, fast_planned[kNumFastConfigs] = {false};
     size_t fast_smem[kNumFastConfigs];
     for (int j = 0; j < kNumFastConfigs; ++j) {
@@ -840,6 +938,10 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
       const int elem = kFastConfigs[j].bits / 8;                  // bytes per row element
       const int align = 16 / elem;                                // row elements per 16 bytes (cp.async / vector stores)
       fast_rowq[j] = (Pmax + kFastConfigs[j].J + align - 1) & ~(align - 1);
+      // pruned kernels: gt + gtail behind every gap table, bmax + pmax per pair slot (odd stride: teams on distinct banks)
+      fast_nb[j] = kFastConfigs[j].prune ? (Pmax + kFastConfigs[j].J - 1) / kFastConfigs[j].J : 0;
+      fast_gq[j] = kGPad + Pmax + kGPad + 2 * fast_nb[j];
+      fast_bm[j] = kFastConfigs[j].prune ? ((2 * fast_nb[j]) | 1) : 0;
       int best_occ = 0;
       // multiples of four only: the DP stages are bound by the ALU pipe of each of the SM's four schedulers, so a
       // scheduler that holds one warp more than the others sets the pace (13 warps: 194 ms on config 3, 12 warps: 169 ms)
@@ -863,8 +965,8 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
           if (!force_w && nw > need_w && nw > 4) continue;
           const int cand_w = cand_per_warp(kFastConfigs[j].bits, nt);
           const size_t d = (size_t)pp.pool_stride + (size_t)(P.max_rec - 1) * pp.g_stride + 2ull * nw * P.max_rec * cand_w;
-          const size_t i = (size_t)(P.max_rec - 1) * fp.gq_stride + fp.kmer_cap + (size_t)nw * nt * slot_words +
-                           2ull * nw * P.max_rec * cand_w + (size_t)nw * nt * P.max_rec;
+          const size_t i = (size_t)(P.max_rec - 1) * fast_gq[j] + fp.kmer_cap + (size_t)nw * nt * slot_words +
+                           2ull * nw * P.max_rec * cand_w + (size_t)nw * nt * P.max_rec + (size_t)nw * nt * fast_bm[j];
           const size_t bytes = d * 8 + i * 4 + sizeof(RecDesc) * P.max_rec + sizeof(FastPlan) + 48 + (size_t)nw * nt * fp.k8_stride;
           if (bytes > (size_t)kMaxSmem) continue;
           const int ctas = (int)std::min<size_t>(233472 / (bytes + 1024), 32);
@@ -963,7 +1065,7 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
         if (!n_b) continue;
         Geo g = make_geo(j, n_b, fast_begin[j]);
         if (kFastConfigs[j].bits == 16) {
-          const int j32 = pick_fast(cl.len - P.sum_len[fast_bucket[j][0]] + 1, 32);
+          const int j32 = pick_fast(cl.len - P.sum_len[fast_bucket[j][0]] + 1, 32, kFastConfigs[j].prune);
           if (allow_retry && j32 >= 0 && plan_config(j32)) {
             Geo r = g;   // same items, same per-item lists; another kernel
             r.j = j32;
@@ -1018,6 +1120,10 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
         const Geo &g = geo[b];
         const int j = g.j, nw = fast_warps[j];
         fp.rowq_stride = fast_rowq[j];
+        fp.gq_stride = fast_gq[j];
+        fp.gt_off = kGPad + Pmax + kGPad;
+        fp.nb_max = fast_nb[j];
+        fp.bm_stride = fast_bm[j];
         fp.cand_w = cand_per_warp(kFastConfigs[j].bits, 32 / kFastConfigs[j].team);
         fp.slotq_stride = fast_slot[j];
         fp.single_row = fast_single[j] ? 1 : 0;
@@ -1038,8 +1144,8 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
         fp.work_counter = lane.work_counter.as<int>();   // one per lane: launches of a lane run in stream order
         CK(cudaMemsetAsync(fp.work_counter, 0, sizeof(int), st));
         if (getenv("FLEMINGO_DEBUG_LAUNCH"))
-          fprintf(stderr, "fast launch%s: cfg bits=%d J=%d team=%d warps=%d ctas/sm=%d grid=%lld items=%lld spc=%d smem=%zu rows=%d\n",
-                  g.retry_of >= 0 ? " (second chance)" : "", kFastConfigs[j].bits, kFastConfigs[j].J, kFastConfigs[j].team, nw,
+          fprintf(stderr, "fast launch%s: cfg bits=%d%s J=%d team=%d warps=%d ctas/sm=%d grid=%lld items=%lld spc=%d smem=%zu rows=%d\n",
+                  g.retry_of >= 0 ? " (second chance)" : "", kFastConfigs[j].bits, kFastConfigs[j].prune ? " pruned" : "", kFastConfigs[j].J, kFastConfigs[j].team, nw,
                   fast_ctas_per_sm[j], g.grid, g.items, g.spc, fast_smem[j], fast_single[j] ? 1 : 2);
         kFastConfigs[j].fn<<<(unsigned)g.grid, nw * 32, fast_smem[j], st>>>(fp);
         CK(cudaGetLastError());

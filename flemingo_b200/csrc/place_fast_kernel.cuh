@@ -86,6 +86,13 @@ struct FastParams {
   long long scratch_slot_stride;  // row elements per pair slot in `scratch` (max_rec * rowq_stride)
   int *work_counter;  // device counter the persistent CTAs claim work items from (zeroed before the launch)
   int n_items;        // organisms of the bucket x chunks
+  // pruned stages (kernels instantiated with PRUNE, see dp_stage_pruned): per connector, behind its gap table, the tile
+  // bounds gt[nb_max] and their suffix maxima gtail[nb_max]; per pair slot, block maxima and prefix maxima of the row
+  int gt_off;         // offset of gt inside a connector's table (ints); gq_stride covers gt_off + 2 * nb_max
+  int nb_max;         // row blocks of the largest organism of the launch: ceil(Pmax / J)
+  int bm_stride;      // ints per pair slot for bmax + pmax (>= 2 * nb_max; 0 in a launch without pruning)
+  int prune_drop;     // a tile belongs to the peak while its bound is within this many energy units of the maximum
+  int prune_frac;     // a stage is pruned when (peak tiles + 2) * prune_frac <= row blocks
 };
 
 struct FastPlan {
@@ -107,12 +114,15 @@ struct FastPlan {
   int err_half[FL_MAX_RECOGNIZERS];      // rounded table entries on a path through recognizer i (half units of error)
   int unit_begin[FL_MAX_RECOGNIZERS];    // first quantisation work unit (table) of recognizer i
   int units;                             // tables of all recognizers (the connectors follow)
+  int prune[FL_MAX_RECOGNIZERS];         // PRUNE kernels: stage of connector c runs dp_stage_pruned, with the peak tiles
+  int dlo[FL_MAX_RECOGNIZERS];           //   dlo[c] .. dhi[c]
+  int dhi[FL_MAX_RECOGNIZERS];
 };
 
 template <class RowT>
 struct FastSmemT {
   double *pool, *G, *cv, *cr;
-  int *Gq, *kmer, *cj, *ca, *cn;
+  int *Gq, *kmer, *cj, *ca, *cn, *bm;
   RowT *rowsq;
   unsigned char *k8;
   RecDesc *rec;
@@ -140,7 +150,8 @@ __device__ __forceinline__ FastSmemT<RowT> carve_fast(const FastParams &f, unsig
   s.cj = reinterpret_cast<int *>(s.rowsq + (size_t)nwarps * nt * f.slotq_stride);  // slot strides are even: 4-byte aligned
   s.ca = s.cj + (size_t)nwarps * p.max_rec * f.cand_w;
   s.cn = s.ca + (size_t)nwarps * p.max_rec * f.cand_w;
-  unsigned char *k8_unaligned = reinterpret_cast<unsigned char *>(s.cn + (size_t)nwarps * nt * p.max_rec);
+  s.bm = s.cn + (size_t)nwarps * nt * p.max_rec;
+  unsigned char *k8_unaligned = reinterpret_cast<unsigned char *>(s.bm + (size_t)nwarps * nt * f.bm_stride);
   s.k8 = k8_unaligned + ((16u - ((unsigned)__cvta_generic_to_shared(k8_unaligned) & 15u)) & 15u);
   return s;
 }
@@ -205,7 +216,7 @@ __device__ __forceinline__ double score_exact_any(const RecDesc &rd, const doubl
 // (a 4-mer group of a PSSM, the bin table of a shape recognizer, a connector); step C (warp 0) adds up the integer
 // ranges, places the sentinel(s) and the thresholds; step D fills the sentinel pads (BITS = 16: and the high halves of
 // the packed gap words).  Contains block barriers.
-template <int BITS, class RowT>
+template <int BITS, class RowT, int J, bool PRUNE>
 __device__ void build_fast_plan(const FastParams &f, const OrgView &v, const FastSmemT<RowT> &sm, int warp, int lane, int nwarps) {
   const PlaceParams &p = f.base;
   FastPlan *plan = sm.plan;
@@ -542,6 +553,45 @@ __device__ void build_fast_plan(const FastParams &f, const OrgView &v, const Fas
         const short sent = (short)plan->sent_stage[c];
         if (!(d >= 0 && d <= P - 2)) Hs[2 * i] = sent;
         Hs[2 * i + 1] = (d - 1 >= 0 && d - 1 <= P - 2) ? Hs[2 * (i - 1)] : sent;
+      }
+    }
+  }
+  // (E) tile bounds of every connector for the pruned stages (dp_stage_pruned), one warp per connector
+  if constexpr (PRUNE) {
+    __syncthreads();
+    if (plan->ok) {
+      const int NB = (P + J - 1) / J;
+      for (int c = warp; c < n - 1; c += nwarps) {
+        const int *Gq = sm.Gq + (size_t)c * f.gq_stride + kGPad;
+        int *gt = sm.Gq + (size_t)c * f.gq_stride + f.gt_off;
+        int *gtail = gt + f.nb_max;
+        const int sent = gq_at<BITS>(Gq, P - 1);   // what every gap outside [0, P-2] holds
+        for (int d = lane; d < NB; d += 32) {
+          const int lo = max(0, (d - 1) * J + 1), hi = min(P - 2, (d + 1) * J - 1);
+          int m = sent;
+          for (int g = lo; g <= hi; ++g) m = max(m, gq_at<BITS>(Gq, g));
+          gt[d] = m;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          int best = gt[NB - 1], dstar = NB - 1;
+          for (int d = NB - 1, run = -0x7fffffff - 1; d >= 0; --d) {
+            run = max(run, gt[d]);
+            gtail[d] = run;
+            if (gt[d] >= best) {   // the smallest offset among equals
+              best = gt[d];
+              dstar = d;
+            }
+          }
+          const double dropd = (double)f.prune_drop * plan->scale;
+          const int drop = dropd < 1.0e9 ? (int)dropd : 1000000000;
+          int dlo = dstar, dhi = dstar;
+          while (dlo > 0 && gt[dlo - 1] >= best - drop) --dlo;
+          while (dhi + 1 < NB && gt[dhi + 1] >= best - drop) ++dhi;
+          plan->dlo[c] = dlo;
+          plan->dhi[c] = dhi;
+          plan->prune[c] = ((dhi - dlo + 1 + 2) * f.prune_frac <= NB) ? 1 : 0;
+        }
       }
     }
   }
@@ -1047,8 +1097,8 @@ __device__ __forceinline__ void add_scores_q(const FastPlan &plan, int r, const 
 
 // (20 warps per CTA for the packed kernel -- its rows are half as large -- were measured: launch bound 640 squeezes it to
 // 86 registers and config 2 takes 2.98 ms instead of 2.85-2.90 ms with 16 warps.)
-template <int J, int TEAM, int BITS>
-__global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
+template <int J, int TEAM, int BITS, bool PRUNE = false>
+__global__ void __launch_bounds__(512, PRUNE ? 1 : 0) place_fast_kernel(const FastParams f) {
   constexpr int NT = 32 / TEAM;
   typedef typename RowOf<BITS>::T RowT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1093,7 +1143,7 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
   const OrgView v = organism_prologue(p, p.org_list[oi], sm.pool, sm.G, sm.rec);
   __syncthreads();
   PHASE_MARK(0);
-  build_fast_plan<BITS, RowT>(f, v, sm, warp, lane, nwarps);
+  build_fast_plan<BITS, RowT, J, PRUNE>(f, v, sm, warp, lane, nwarps);
   __syncthreads();
   PHASE_MARK(1);
 
@@ -1143,7 +1193,21 @@ __global__ void __launch_bounds__(512) place_fast_kernel(const FastParams f) {
         const RowT *prev = f.single_row ? rowsq : rowsq + (size_t)((i - 1) & 1) * f.rowq_stride;
         RowT *cur = f.single_row ? rowsq : rowsq + (size_t)(i & 1) * f.rowq_stride;
         const int *Gq = sm.Gq + (size_t)(i - 1) * f.gq_stride + kGPad;
-        if constexpr (BITS == 16)
+        bool pruned = false;
+        if constexpr (PRUNE) {
+          if (plan.prune[i - 1]) {   // uniform over the CTA: a property of the organism's connector
+            pruned = true;
+            PruneTabs tabs;
+            tabs.gt = sm.Gq + (size_t)(i - 1) * f.gq_stride + f.gt_off;
+            tabs.gtail = tabs.gt + f.nb_max;
+            tabs.dlo = plan.dlo[i - 1];
+            tabs.dhi = plan.dhi[i - 1];
+            int *bm = sm.bm + (size_t)slot * f.bm_stride;
+            dp_stage_pruned<J, TEAM, RowT>(prev, cur, Gq, tabs, bm, bm + f.nb_max, P, tl);
+          }
+        }
+        if (pruned) {
+        } else if constexpr (BITS == 16)
           dp_stage16<J, TEAM>(prev, cur, reinterpret_cast<const unsigned *>(Gq), P, tl);
         else
           // accumulators start at the lowest int, NOT at the sentinel: the sentinel only has to lie below the legit gap

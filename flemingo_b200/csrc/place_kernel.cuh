@@ -17,6 +17,7 @@
 //   so every lane executes the same number of tiles; both jobs run through ONE loop so the warp never diverges
 //   in the hot code.
 #pragma once
+#include <type_traits>
 
 #define T_MGW 0
 #define T_PROT 1024
@@ -442,6 +443,185 @@ __device__ __forceinline__ void dp_stage16(const short *prev, short *cur, const 
     if (st.kstep) flush16<J>(acc, cur, st.b);
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Pruned stage: the same cur[j] = max_{k<=j} (prev[k] + G[j-k]) with the tiles that cannot matter left out -- exactly.
+//
+// A tile (row block b, k block kb, delta = b - kb) only holds gaps in [(delta-1)J+1, (delta+1)J-1], so every cell of it
+// is at most  bmax[kb] + gt[delta]  (bmax = maximum of prev over the k block, gt = maximum of G over that gap range).
+// Once the rows of block b hold some values, a tile whose bound does not exceed the SMALLEST of them cannot raise any
+// of the J maxima and is skipped; the rows come out bit-identical to dp_stage.  What makes this pay is a connector whose
+// gap energies fall off quickly around their peak (small sigma): the tiles around the peak [dlo, dhi] are run first and
+// unconditionally, which lifts the J maxima to their final level or close to it, and then
+//   near side (delta < dlo): one bound test per tile;
+//   far side  (delta > dhi): first ONE test for the whole rest, pmax[kb] + gtail[delta] (prefix maximum of prev, suffix
+//                            maximum of gt), then tile by tile.
+// The per-connector tables gt / gtail / dlo / dhi come from the organism's plan; bmax / pmax are built here, per pair
+// and stage.  Row blocks are not folded (the work per block no longer grows with b): a round gives one block to each
+// lane of the team, top blocks first, and flushes after the round -- lower rounds only read lower k blocks, so the
+// stage may run in place like dp_stage.  The lanes of a warp leave the tile loop together (ballot), whatever their
+// number of tiles.
+// ------------------------------------------------------------------------------------------------
+template <int J, class Op>
+__device__ __forceinline__ void tile_any(typename Op::T (&acc)[J], const typename Op::T *prev,
+                                         const typename Op::T *__restrict__ G, int b, int kb) {
+  typedef typename Op::T T;
+  // A[i] = G[m + J-1 - i], B[i] = G[m - 1 - i], m = (b - kb) * J; on the diagonal tile (m = 0) B is the sentinel pad
+  const T *ga = G + (b - kb) * J + (J - 1);
+  const T *pk = prev + kb * J;
+  T A[J], B[J], pv[J];
+#pragma unroll
+  for (int u = 0; u < J; ++u) {
+    A[u] = ga[-u];
+    B[u] = ga[-J - u];
+    pv[u] = pk[u];
+  }
+#pragma unroll
+  for (int u = 0; u < J; ++u) {
+#pragma unroll
+    for (int t = 0; t < J; ++t) {
+      const T g = (u <= t) ? A[J - 1 - t + u] : B[u - t - 1];
+      acc[t] = Op::cell(acc[t], pv[u], g);
+    }
+  }
+}
+
+template <int J>
+__device__ __forceinline__ void tile_any16(unsigned (&acc)[J], const short *prev, const unsigned *__restrict__ H, int b, int kb) {
+  const unsigned *ha = H + (b - kb) * J + (J - 1);
+  const unsigned *pk = reinterpret_cast<const unsigned *>(prev + kb * J);
+  unsigned A[J], B[J], pv[J / 2];
+#pragma unroll
+  for (int u = 0; u < J; ++u) {
+    A[u] = ha[-u];
+    B[u] = ha[-J - u];
+  }
+#pragma unroll
+  for (int u = 0; u < J / 2; ++u) pv[u] = pk[u];
+#pragma unroll
+  for (int u = 0; u < J / 2; ++u) {
+#pragma unroll
+    for (int t = 0; t < J; ++t) {
+      const unsigned h = (t >= 2 * u) ? A[J - 1 - t + 2 * u] : B[2 * u - t - 1];
+      acc[t] = __viaddmax_s16x2(pv[u], h, acc[t]);
+    }
+  }
+}
+
+struct PruneTabs {
+  const int *gt;     // [NB] bound of G over the gap range of tile offset delta
+  const int *gtail;  // [NB] max of gt[delta..]
+  int dlo, dhi;      // tile offsets run unconditionally (around the peak of G)
+};
+
+// The next k block at or below kb (walking down) whose tile can still raise one of the maxima of row block b, given
+// the smallest of them so far; -1 when none is left.  Tiles dlo..dhi have been run already.
+__device__ __forceinline__ int prune_next_tile(int b, int kb, int minacc, const PruneTabs &tabs, const int *bm, const int *pm) {
+  while (kb >= 0) {
+    const int d = b - kb;
+    if (d >= tabs.dlo && d <= tabs.dhi) {
+      kb = b - tabs.dhi - 1;
+      continue;
+    }
+    if (d > tabs.dhi && pm[kb] + tabs.gtail[d] <= minacc) return -1;  // nothing on the far side can matter any more
+    if (bm[kb] + tabs.gt[d] > minacc) break;
+    --kb;
+  }
+  return kb;
+}
+
+// smallest maximum among the rows of block b that exist (j < P)
+template <int J>
+__device__ __forceinline__ int prune_row_min(const int (&acc)[J], int b, int P) {
+  int mn = 0x7fffffff;
+#pragma unroll
+  for (int t = 0; t < J; ++t) mn = min(mn, (b * J + t < P) ? acc[t] : 0x7fffffff);
+  return mn;
+}
+template <int J>
+__device__ __forceinline__ int prune_row_min(const unsigned (&acc)[J], int b, int P) {
+  int mn = 0x7fffffff;
+#pragma unroll
+  for (int t = 0; t < J; ++t) {
+    const int lo = (int)(short)(acc[t] & 0xffffu), hi = (int)(short)(acc[t] >> 16);
+    mn = min(mn, (b * J + t < P) ? (lo > hi ? lo : hi) : 0x7fffffff);
+  }
+  return mn;
+}
+template <int J>
+__device__ __forceinline__ void prune_run_tile(int (&acc)[J], const int *prev, const int *__restrict__ G, int b, int kb) {
+  tile_any<J, OpI32>(acc, prev, G, b, kb);
+}
+template <int J>
+__device__ __forceinline__ void prune_run_tile(unsigned (&acc)[J], const short *prev, const int *__restrict__ G, int b, int kb) {
+  tile_any16<J>(acc, prev, reinterpret_cast<const unsigned *>(G), b, kb);
+}
+template <int J>
+__device__ __forceinline__ void prune_flush(const int (&acc)[J], int *cur, int b) {
+  int *dst = cur + b * J;
+#pragma unroll
+  for (int t = 0; t < J; ++t) dst[t] = acc[t];
+}
+template <int J>
+__device__ __forceinline__ void prune_flush(const unsigned (&acc)[J], short *cur, int b) {
+  flush16<J>(acc, cur, b);
+}
+
+#ifdef __CUDACC__
+// RowT = int (G = int table) or short (G = packed words H).  bm / pm: NB ints each, per pair.
+template <int J, int TEAM, class RowT>
+__device__ __forceinline__ void dp_stage_pruned(const RowT *prev, RowT *cur, const int *__restrict__ G, const PruneTabs tabs,
+                                                int *bm, int *pm, int P, int tl) {
+  constexpr bool k16 = sizeof(RowT) == 2;
+  constexpr int kLow = -0x7fffffff - 1;
+  typedef typename std::conditional<k16, unsigned, int>::type AccT;
+  const int NB = (P + J - 1) / J;
+  // block maxima and their prefix maxima (entries k >= P of the last block are padding, not values)
+  for (int r0 = 0, carry = kLow; r0 < NB; r0 += TEAM) {
+    const int kb = r0 + tl;
+    int v = kLow;
+    if (kb < NB) {
+      const RowT *pk = prev + kb * J;
+#pragma unroll
+      for (int u = 0; u < J; ++u) v = max(v, (kb * J + u < P) ? (int)pk[u] : kLow);
+      bm[kb] = v;
+    }
+#pragma unroll
+    for (int o = 1; o < TEAM; o <<= 1) {
+      const int w = __shfl_up_sync(0xffffffffu, v, o, TEAM);
+      if (tl >= o) v = max(v, w);
+    }
+    v = max(v, carry);
+    if (kb < NB) pm[kb] = v;
+    carry = __shfl_sync(0xffffffffu, v, TEAM - 1, TEAM);
+  }
+  __syncwarp();
+  for (int hi = NB - 1; hi >= 0; hi -= TEAM) {
+    const int b = hi - tl;   // < 0: idle lane of the last round
+    AccT acc[J];
+#pragma unroll
+    for (int t = 0; t < J; ++t) acc[t] = k16 ? (AccT)kLowest16x2 : (AccT)kLow;
+    // the tiles around the peak
+    for (int d = tabs.dlo; d <= tabs.dhi; ++d)
+      if (b >= 0 && d <= b) prune_run_tile<J>(acc, prev, G, b, b - d);
+    int minacc = (b >= 0 && tabs.dlo <= b) ? prune_row_min<J>(acc, b, P) : kLow;
+    // everything else, by bound
+    int kb = b;
+    for (;;) {
+      kb = prune_next_tile(b, kb, minacc, tabs, bm, pm);
+      if (!__any_sync(0xffffffffu, kb >= 0)) break;
+      if (kb >= 0) {
+        prune_run_tile<J>(acc, prev, G, b, kb);
+        minacc = prune_row_min<J>(acc, b, P);
+        --kb;
+      }
+    }
+    __syncwarp();
+    if (b >= 0) prune_flush<J>(acc, cur, b);
+    __syncwarp();
+  }
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // Shared pieces of the placement kernels

@@ -73,8 +73,9 @@ def assemble(org_id, recognizers, connectors) -> objects.OrganismObject:
 
 
 def pssm_organisms(n_org: int, max_seq_length: int, seed: int, n_rec: int = 3, rec_len: int = 12,
-                   mu_range=None) -> list:
-    """Config 2 / config 4 organisms: n_rec PSSM recognizers of rec_len columns."""
+                   mu_range=None, sigma_range=None) -> list:
+    """Config 2 / config 4 organisms: n_rec PSSM recognizers of rec_len columns.  sigma_range: connector sigmas drawn
+    uniformly from it instead of the factory's exponential (tight connectors, as fitted organisms have)."""
     rng = np.random.default_rng(seed)
     out = []
     for o in range(n_org):
@@ -82,12 +83,13 @@ def pssm_organisms(n_org: int, max_seq_length: int, seed: int, n_rec: int = 3, r
         cons = []
         for _ in range(n_rec - 1):
             mu = None if mu_range is None else float(rng.uniform(*mu_range))
-            cons.append(random_connector(rng, max_seq_length, mu))
+            sigma = None if sigma_range is None else float(rng.uniform(*sigma_range))
+            cons.append(random_connector(rng, max_seq_length, mu, sigma))
         out.append(assemble(o, recs, cons))
     return out
 
 
-def mixed_organisms(n_org: int, max_seq_length: int, seed: int, max_rec: int = 6, p_pssm: float = 0.5) -> list:
+def mixed_organisms(n_org: int, max_seq_length: int, seed: int, max_rec: int = 6, p_pssm: float = 0.5, sigma_range=None) -> list:
     """Config 3 organisms: n ~ U{1..max_rec}; each recognizer a PSSM (L ~ U{4..12}) with prob p_pssm, else a
     shape recognizer (uniform type, L ~ U{5..9})."""
     ensure_null_models()
@@ -101,7 +103,10 @@ def mixed_organisms(n_org: int, max_seq_length: int, seed: int, max_rec: int = 6
                 recs.append(random_pssm(rng, int(rng.integers(4, 13))))
             else:
                 recs.append(random_shape(rng))
-        cons = [random_connector(rng, max_seq_length) for _ in range(n - 1)]
+        if sigma_range is None:
+            cons = [random_connector(rng, max_seq_length) for _ in range(n - 1)]
+        else:
+            cons = [random_connector(rng, max_seq_length, None, float(rng.uniform(*sigma_range))) for _ in range(n - 1)]
         out.append(assemble(o, recs, cons))
     return out
 

@@ -39,13 +39,15 @@ def golden_cases(golden, golden_null_models):
     return [(case, build_case_organism(case)) for case in golden["cases"]]
 
 
-@pytest.fixture(scope="session", params=["filter+refine", "filter+refine, one row", "filter+refine, int32 only", "exact-only"])
+@pytest.fixture(scope="session", params=["filter+refine", "filter+refine, one row", "filter+refine, int32 only",
+                                         "filter+refine, pruned stages", "filter+refine, pruned stages, one row", "exact-only"])
 def engine(request):
     """The process-wide engine in its kernel modes -- the integer filter pass as the host plans it (packed 16-bit DPX
     where the organism's value range allows it, int32 otherwise; two quantised rows per pair in shared memory), the same
     with ONE row (in-place DP stages; chosen automatically only when it lets more warps live on an SM, forced here), the
-    int32 arithmetic for every organism, and every pair through the exact fp64 kernel.  All of them must reproduce the
-    reference bit for bit."""
+    int32 arithmetic for every organism, every organism through the kernels with pruned DP stages (dp_stage_pruned; chosen
+    automatically only for organisms with tight connectors) with two rows and in place, and every pair through the exact
+    fp64 kernel.  All of them must reproduce the reference bit for bit."""
     import os
     import torch
     if not torch.cuda.is_available():
@@ -57,7 +59,10 @@ def engine(request):
         os.environ["FLEMINGO_FAST_ROWS"] = "1"      # read by fl_place_batch at every call
     if request.param.endswith("int32 only"):
         os.environ["FLEMINGO_FAST_BITS"] = "32"
+    if "pruned stages" in request.param:
+        os.environ["FLEMINGO_PRUNE"] = "2"
     yield eng
+    os.environ.pop("FLEMINGO_PRUNE", None)
     os.environ.pop("FLEMINGO_FAST_ROWS", None)
     os.environ.pop("FLEMINGO_FAST_BITS", None)
     eng.exact_only = False

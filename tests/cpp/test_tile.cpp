@@ -27,6 +27,8 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) {
   for (int i = 0; i < 4; i++) r |= (unsigned)((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xff) << (8 * i);
   return r;
 }
+#include <type_traits>
+static long long g_tiles_run = 0, g_tiles_all = 0;
 #include TILE_EXTRACT
 template <int J, int TEAM> int run_i32(int P, unsigned seed) {
   srand(seed);
@@ -147,6 +149,90 @@ template <int J, int TEAM> int run_i16(int P, unsigned seed, bool inplace) {
   for (int j = 0; j < P; j++) if (cur[j] != ref[j]) bad++;
   return bad;
 }
+
+// Pruned stage (dp_stage_pruned): same rows as the naive recurrence whatever the gap profile -- peaked (where the
+// pruning bites), flat (where every tile runs) or random -- in place, the lanes of a round flushing together after the
+// round the way the kernel does.  The tables gt / gtail / dlo / dhi are built like build_fast_plan step E builds them.
+template <int J, int TEAM, bool K16> int run_pruned(int P, unsigned seed, int profile) {
+  srand(seed);
+  typedef typename std::conditional<K16, short, int>::type RowT;
+  typedef typename std::conditional<K16, unsigned, int>::type AccT;
+  const int SENT = K16 ? -20000 : -50000000, AMP = K16 ? 6000 : 1000000;
+  const int NB = (P + J - 1) / J, NBJ = NB * J;
+  std::vector<RowT> row(NBJ + 64, 0);
+  std::vector<int> G(P + 2 * kGPad + 2, SENT), ref(P);
+  for (int i = 0; i < P; i++) row[i] = (RowT)(-(rand() % AMP));
+  const int mu = rand() % (P + 20), width = 1 + rand() % 12;
+  for (int i = 0; i + 1 < P; i++) {
+    int g;
+    if (profile == 0) g = -(int)std::min((double)(AMP - 1), (double)(i - mu) * (i - mu) * AMP / (8.0 * width * width)) - rand() % 3;  // peaked, floor at -AMP
+    else if (profile == 1) g = -(rand() % 4);                                                                                // flat
+    else g = -(rand() % AMP);                                                                                                // random
+    G[kGPad + i] = g;
+  }
+  for (int j = 0; j < P; j++) { int b = -0x7fffffff; for (int k = 0; k <= j; k++) b = std::max(b, (int)row[k] + G[kGPad + j - k]); ref[j] = b; }
+  std::vector<unsigned> H(G.size());
+  for (int i = 1; i < (int)H.size(); i++) H[i] = pack16(G[i], G[i - 1]);
+  H[0] = pack16(G[0], SENT);
+  const int *Gp = K16 ? reinterpret_cast<const int *>(H.data()) + kGPad : G.data() + kGPad;
+  // step E of the plan
+  std::vector<int> gt(NB), gtail(NB), bm(NB), pm(NB);
+  for (int d = 0; d < NB; d++) {
+    const int lo = std::max(0, (d - 1) * J + 1), hi = std::min(P - 2, (d + 1) * J - 1);
+    int m = SENT;
+    for (int g = lo; g <= hi; g++) m = std::max(m, G[kGPad + g]);
+    gt[d] = m;
+  }
+  int best = gt[NB - 1], dstar = NB - 1;
+  for (int d = NB - 1, run = -0x7fffffff - 1; d >= 0; d--) {
+    run = std::max(run, gt[d]);
+    gtail[d] = run;
+    if (gt[d] >= best) { best = gt[d]; dstar = d; }
+  }
+  const int drop = AMP / 8;
+  PruneTabs tabs;
+  tabs.gt = gt.data();
+  tabs.gtail = gtail.data();
+  tabs.dlo = tabs.dhi = dstar;
+  while (tabs.dlo > 0 && gt[tabs.dlo - 1] >= best - drop) --tabs.dlo;
+  while (tabs.dhi + 1 < NB && gt[tabs.dhi + 1] >= best - drop) ++tabs.dhi;
+  for (int kb = 0, run = -0x7fffffff - 1; kb < NB; kb++) {
+    int v = -0x7fffffff - 1;
+    for (int u = 0; u < J; u++) if (kb * J + u < P) v = std::max(v, (int)row[kb * J + u]);
+    bm[kb] = v;
+    run = std::max(run, v);
+    pm[kb] = run;
+  }
+  long long tiles = 0;
+  RowT *buf = row.data();
+  for (int hi = NB - 1; hi >= 0; hi -= TEAM) {
+    AccT acc[TEAM][J];
+    for (int tl = 0; tl < TEAM; tl++) {
+      const int b = hi - tl;
+      if (b < 0) continue;
+      for (int t = 0; t < J; t++) acc[tl][t] = K16 ? (AccT)kLowest16x2 : (AccT)(-0x7fffffff - 1);
+      for (int d = tabs.dlo; d <= tabs.dhi; d++)
+        if (d <= b) { prune_run_tile<J>(acc[tl], buf, Gp, b, b - d); tiles++; }
+      int minacc = (tabs.dlo <= b) ? prune_row_min<J>(acc[tl], b, P) : -0x7fffffff - 1;
+      int kb = b;
+      for (;;) {
+        kb = prune_next_tile(b, kb, minacc, tabs, bm.data(), pm.data());
+        if (kb < 0) break;
+        prune_run_tile<J>(acc[tl], buf, Gp, b, kb);
+        tiles++;
+        minacc = prune_row_min<J>(acc[tl], b, P);
+        --kb;
+      }
+    }
+    for (int tl = 0; tl < TEAM; tl++)
+      if (hi - tl >= 0) prune_flush<J>(acc[tl], buf, hi - tl);
+  }
+  int bad = 0;
+  for (int j = 0; j < P; j++) if ((int)buf[j] != ref[j]) bad++;
+  g_tiles_run += tiles;
+  g_tiles_all += (long long)NB * (NB + 1) / 2;
+  return bad;
+}
 template <int J> int run(int P, unsigned seed) {
   srand(seed);
   int NBJ = ((P + J - 1) / J) * J;
@@ -171,9 +257,14 @@ int main() {
     for (int ip = 0; ip < 2 && P >= 2; ip++)   // P = 1 has no legit gap: the integer pass never sees it (FastPlan.ok)
       b += run_i16<18, 8>(P, P + 20, ip) + run_i16<14, 8>(P, P + 21, ip) + run_i16<10, 16>(P, P + 22, ip) + run_i16<6, 8>(P, P + 23, ip) +
            run_i16<22, 32>(P, P + 24, ip) + run_i16<18, 16>(P, P + 25, ip) + run_i16<2, 8>(P, P + 26, ip);
+    for (int prof = 0; prof < 3 && P >= 2; prof++)
+      b += run_pruned<9, 8, false>(P, P + 30 + prof, prof) + run_pruned<13, 16, false>(P, P + 33 + prof, prof) + run_pruned<17, 32, false>(P, P + 36 + prof, prof) +
+           run_pruned<10, 8, true>(P, P + 39 + prof, prof) + run_pruned<14, 16, true>(P, P + 42 + prof, prof) + run_pruned<18, 32, true>(P, P + 45 + prof, prof) +
+           run_pruned<3, 8, false>(P, P + 48 + prof, prof) + run_pruned<2, 8, true>(P, P + 51 + prof, prof);
     if (b) printf("P=%d bad=%d\n", P, b);
     total += b;
   }
+  printf("pruned stages ran %lld of %lld tiles\n", g_tiles_run, g_tiles_all);
   printf("total bad %d\n", total);
   return total != 0;
 }

@@ -15,6 +15,13 @@ from flemingo_b200.engine import Engine  # noqa: E402
 from tests.helpers import adversarial_workload  # noqa: E402
 
 
+# as planned / one arithmetic forced on every organism / the kernels with pruned stages forced on every organism
+MODES = ("auto", "forced-16", "forced-32", "pruned-16", "pruned-32", "pruned-1row", "unpruned")
+MODE_ENV = {"auto": {}, "forced-16": {"FLEMINGO_FAST_BITS": "16"}, "forced-32": {"FLEMINGO_FAST_BITS": "32"},
+            "pruned-16": {"FLEMINGO_FAST_BITS": "16", "FLEMINGO_PRUNE": "2"}, "pruned-32": {"FLEMINGO_FAST_BITS": "32", "FLEMINGO_PRUNE": "2"},
+            "pruned-1row": {"FLEMINGO_PRUNE": "2", "FLEMINGO_FAST_ROWS": "1"}, "unpruned": {"FLEMINGO_PRUNE": "0"}}
+
+
 def random_population(rng, S, ragged):
     orgs = []
     for o in range(int(rng.integers(8, 40))):
@@ -96,13 +103,14 @@ def main():
             continue
         eng.exact_only = False
         stats = []
-        for mode in ("auto", "16", "32"):
-            if mode != "auto":
-                os.environ["FLEMINGO_FAST_BITS"] = mode
+        for mode in MODES:
+            env = MODE_ENV[mode]
+            os.environ.update(env)
             eng.path_stats()
             got = eng.place(sset, trace=True)
             stats.append(eng.path_stats(detail=True))
-            os.environ.pop("FLEMINGO_FAST_BITS", None)
+            for key in env:
+                os.environ.pop(key, None)
             for k in ("energies", "gaps", "rec_scores", "con_scores"):
                 a, b = getattr(got, k), getattr(want, k)
                 if not np.array_equal(a, b, equal_nan=True):
@@ -110,8 +118,8 @@ def main():
                     raise SystemExit(f"round {r} S={S} mode {mode}: {k} differs at {bad.tolist()}")
         total += want.energies.size
         print(f"round {r:3d} S={S:3d} {len(orgs):3d} organisms x {len(seqs):3d} sequences: equal in all modes; "
-              f"(filter pairs, exact kernel, second chance) auto {stats[0]} forced-16 {stats[1]} forced-32 {stats[2]}", flush=True)
-    print(f"fuzz ok: {total} pairs x 3 modes bit-identical to the exact kernel")
+              f"(filter pairs, exact kernel, second chance) " + " ".join(f"{m} {st}" for m, st in zip(MODES, stats)), flush=True)
+    print(f"fuzz ok: {total} pairs x {len(MODES)} modes bit-identical to the exact kernel")
 
 
 if __name__ == "__main__":
