@@ -1217,7 +1217,8 @@ extern "C" int fl_path_stats(fl_ctx *ctx, long long *fast_pairs, long long *fall
     static const char *names[16] = {"prologue", "plan", "unpack", "scores", "dp_stage", "refine(5)", "misc", "claim/tail", "refine(1)", "refine(2)", "refine(3)", "refine(4)", "", "", "", ""};
     double tot = 0;
     for (int i = 0; i < 12; ++i) tot += (double)clk[i];
-    fprintf(stderr, "stage scans: all-single %llu, mixed %llu, candidates %llu\n", clk[12], clk[13], clk[14]);
+    fprintf(stderr, "pruned stages: %llu pair-stages ran %llu of %llu tiles (%.1f %%) in %llu lane slots (%.1f %% of the slots ran a tile)\n", clk[14], clk[12], clk[13],
+            clk[13] ? 100.0 * (double)clk[12] / (double)clk[13] : 0.0, clk[15], clk[15] ? 100.0 * (double)clk[12] / (double)clk[15] : 0.0);
     for (int i = 0; i < 12; ++i) fprintf(stderr, "phase %-10s %14llu ticks %5.1f %%\n", names[i], clk[i], tot > 0 ? 100.0 * clk[i] / tot : 0.0);
     unsigned long long zero[16] = {0};
     CK(cudaMemcpyToSymbol(g_phase_clk, zero, sizeof zero));

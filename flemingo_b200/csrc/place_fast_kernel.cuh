@@ -1098,7 +1098,7 @@ __device__ __forceinline__ void add_scores_q(const FastPlan &plan, int r, const 
 // (20 warps per CTA for the packed kernel -- its rows are half as large -- were measured: launch bound 640 squeezes it to
 // 86 registers and config 2 takes 2.98 ms instead of 2.85-2.90 ms with 16 warps.)
 template <int J, int TEAM, int BITS, bool PRUNE = false>
-__global__ void __launch_bounds__(512, PRUNE ? 1 : 0) place_fast_kernel(const FastParams f) {
+__global__ void __launch_bounds__(512, 1) place_fast_kernel(const FastParams f) {
   constexpr int NT = 32 / TEAM;
   typedef typename RowOf<BITS>::T RowT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1203,7 +1203,24 @@ __global__ void __launch_bounds__(512, PRUNE ? 1 : 0) place_fast_kernel(const Fa
             tabs.dlo = plan.dlo[i - 1];
             tabs.dhi = plan.dhi[i - 1];
             int *bm = sm.bm + (size_t)slot * f.bm_stride;
-            dp_stage_pruned<J, TEAM, RowT>(prev, cur, Gq, tabs, bm, bm + f.nb_max, P, tl);
+            const int tiles_run = dp_stage_pruned<J, TEAM, RowT>(prev, cur, Gq, tabs, bm, bm + f.nb_max, P, tl);
+#ifdef FL_PHASE_CLOCKS
+            {   // tiles run / tiles of the full triangle / pruned pair-stages
+              int sum = live ? (tiles_run & 0xffff) : 0;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+              if (lane == 0) atomicAdd(&g_phase_clk[15], 32ull * (unsigned long long)(tiles_run >> 16));
+              const unsigned live_teams = __popc(__ballot_sync(0xffffffffu, live && tl == 0));
+              if (lane == 0) {
+                const unsigned long long nb = (unsigned long long)((P + J - 1) / J);
+                atomicAdd(&g_phase_clk[12], (unsigned long long)sum);
+                atomicAdd(&g_phase_clk[13], live_teams * (nb * (nb + 1) / 2));
+                atomicAdd(&g_phase_clk[14], (unsigned long long)live_teams);
+              }
+            }
+#else
+            (void)tiles_run;
+#endif
           }
         }
         if (pruned) {

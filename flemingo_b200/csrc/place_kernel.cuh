@@ -569,13 +569,15 @@ __device__ __forceinline__ void prune_flush(const unsigned (&acc)[J], short *cur
 
 #ifdef __CUDACC__
 // RowT = int (G = int table) or short (G = packed words H).  bm / pm: NB ints each, per pair.
+// Returns tiles this lane ran + 65536 * tile steps of the warp (statistics of the profiling build; dead code otherwise).
 template <int J, int TEAM, class RowT>
-__device__ __forceinline__ void dp_stage_pruned(const RowT *prev, RowT *cur, const int *__restrict__ G, const PruneTabs tabs,
-                                                int *bm, int *pm, int P, int tl) {
+__device__ __forceinline__ int dp_stage_pruned(const RowT *prev, RowT *cur, const int *__restrict__ G, const PruneTabs tabs,
+                                               int *bm, int *pm, int P, int tl) {
   constexpr bool k16 = sizeof(RowT) == 2;
   constexpr int kLow = -0x7fffffff - 1;
   typedef typename std::conditional<k16, unsigned, int>::type AccT;
   const int NB = (P + J - 1) / J;
+  int tiles_run = 0;
   // block maxima and their prefix maxima (entries k >= P of the last block are padding, not values)
   for (int r0 = 0, carry = kLow; r0 < NB; r0 += TEAM) {
     const int kb = r0 + tl;
@@ -602,16 +604,23 @@ __device__ __forceinline__ void dp_stage_pruned(const RowT *prev, RowT *cur, con
 #pragma unroll
     for (int t = 0; t < J; ++t) acc[t] = k16 ? (AccT)kLowest16x2 : (AccT)kLow;
     // the tiles around the peak
-    for (int d = tabs.dlo; d <= tabs.dhi; ++d)
-      if (b >= 0 && d <= b) prune_run_tile<J>(acc, prev, G, b, b - d);
+    for (int d = tabs.dlo; d <= tabs.dhi; ++d) {
+      tiles_run += 65536;
+      if (b >= 0 && d <= b) {
+        prune_run_tile<J>(acc, prev, G, b, b - d);
+        ++tiles_run;
+      }
+    }
     int minacc = (b >= 0 && tabs.dlo <= b) ? prune_row_min<J>(acc, b, P) : kLow;
     // everything else, by bound
     int kb = b;
     for (;;) {
       kb = prune_next_tile(b, kb, minacc, tabs, bm, pm);
       if (!__any_sync(0xffffffffu, kb >= 0)) break;
+      tiles_run += 65536;
       if (kb >= 0) {
         prune_run_tile<J>(acc, prev, G, b, kb);
+        ++tiles_run;
         minacc = prune_row_min<J>(acc, b, P);
         --kb;
       }
@@ -620,6 +629,7 @@ __device__ __forceinline__ void dp_stage_pruned(const RowT *prev, RowT *cur, con
     if (b >= 0) prune_flush<J>(acc, cur, b);
     __syncwarp();
   }
+  return tiles_run;
 }
 #endif
 

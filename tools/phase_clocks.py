@@ -1,5 +1,5 @@
 """Per-phase SM-clock breakdown of place_fast_kernel (profiling build with -DFL_PHASE_CLOCKS, see tools/phase_clocks.sh).
-Usage: python tools/phase_clocks.py [c2|c3]   -- the library must have been built with -DFL_PHASE_CLOCKS."""
+Usage: python tools/phase_clocks.py [c2|c3|tight|tight-mixed]   -- the library must have been built with -DFL_PHASE_CLOCKS."""
 import sys
 sys.path.insert(0, ".")
 import torch  # noqa: F401  (CUDA runtime initialisation order as in bench.py)
@@ -9,7 +9,14 @@ _cabi.LIB_PATH = Path("tools/_phase_lib/libflemingo_b200.so").resolve()   # the 
 from flemingo_b200.engine import Engine
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "c2"
-orgs, pos, neg = synthetic.make_workload(wl)
+if wl == "tight":     # config 2 with connector sigmas from config.json's bounds [1, 3] (tools/bench_tight.py)
+    _, pos, neg = synthetic.make_workload("c2")
+    orgs = synthetic.pssm_organisms(256, 300, 3, sigma_range=(1.0, 3.0))
+elif wl == "tight-mixed":
+    _, pos, neg = synthetic.make_workload("c2")
+    orgs = synthetic.mixed_organisms(256, 300, 3, sigma_range=(1.0, 3.0))
+else:
+    orgs, pos, neg = synthetic.make_workload(wl)
 eng = Engine(0)
 for _ in range(2):
     eng.evaluate(orgs, pos, neg, "Welch", 0.2)
