@@ -180,6 +180,7 @@ struct DevBuf {
 
 struct SeqClass {
   int len, begin, count;
+  float low_share = 0.f;  // share of low-complexity sequences in a sample of the class (see low_complexity)
 };
 
 struct SeqSet {
@@ -378,6 +379,40 @@ static bool is_pinned(const void *p) {
   return a.type != cudaMemoryTypeUnregistered;
 }
 
+// Low-complexity sequence (2-letter alphabets, short-period repeats): fewer than 0.4 of the distinct 4-mers a random
+// sequence of the same length would show.  On such sequences the recognizer scores are periodic, every k block holds a
+// good predecessor and the pruned stages (dp_stage_pruned) prune nothing while paying for their small tiles, so a length
+// class with many of them keeps the regular kernels.  A routing heuristic only: results do not depend on it.
+static bool low_complexity(const char *s, int L) {
+  unsigned long long seen[4] = {0, 0, 0, 0};
+  int code = 0, valid = 0, distinct = 0, total = 0;
+  for (int i = 0; i < L; ++i) {
+    int b;
+    switch (s[i]) {
+      case 'a': case 'A': b = 0; break;
+      case 'g': case 'G': b = 1; break;
+      case 'c': case 'C': b = 2; break;
+      case 't': case 'T': b = 3; break;
+      default: b = -1;
+    }
+    if (b < 0) {
+      valid = 0;
+      continue;
+    }
+    code = ((code << 2) | b) & 255;
+    if (++valid >= 4) {
+      ++total;
+      const unsigned long long bit = 1ULL << (code & 63);
+      if (!(seen[code >> 6] & bit)) {
+        seen[code >> 6] |= bit;
+        ++distinct;
+      }
+    }
+  }
+  if (total < 12) return false;
+  return distinct < 0.4 * 256.0 * (1.0 - std::exp(-total / 256.0));
+}
+
 static int upload_sequences(fl_ctx *ctx, SeqSet &set, const char *bytes, const long long *offsets, int n_seq) {
   if (n_seq < 0 || (n_seq > 0 && (!bytes || !offsets))) return fail(FL_E_ARG, "fl_upload_sequences: bad arguments");
   std::vector<int> len(n_seq), word_off(n_seq), unk_off(n_seq), order(n_seq), k8_off(n_seq);
@@ -403,6 +438,15 @@ static int upload_sequences(fl_ctx *ctx, SeqSet &set, const char *bytes, const l
     const int l = len[order[i]];
     if (set.classes.empty() || set.classes.back().len != l) set.classes.push_back({l, i, 0});
     set.classes.back().count++;
+  }
+  for (SeqClass &cl : set.classes) {  // up to 64 sequences per class, evenly spread
+    const int n_sample = std::min(cl.count, 64);
+    int low = 0;
+    for (int k = 0; k < n_sample; ++k) {
+      const int sq = order[cl.begin + (int)((long long)k * cl.count / n_sample)];
+      if (low_complexity(bytes + offsets[sq], len[sq])) ++low;
+    }
+    cl.low_share = (float)low / (float)n_sample;
   }
   set.n_seq = n_seq;
   const size_t raw_bytes = n_seq ? (size_t)(offsets[n_seq] - offsets[0]) : 0;
@@ -882,11 +926,13 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
     std::map<long long, double> den_cache;
     std::vector<int> exact_bucket[kNumTileSizes], fast_bucket[kNumFastConfigs];
     long long n_fast_org = 0;
+    // by estimate: not on a length class with many low-complexity sequences (see low_complexity)
+    const int prune_mode_c = (prune_mode == 1 && cl.low_share > 0.15f) ? 0 : prune_mode;
     for (int o = 0; o < n_org; ++o) {
       const int Po = cl.len - P.sum_len[o] + 1;
       if (allow_fast && P.kmer_need[o] > 0 && P.kmer_need[o] <= 16384 && Po >= 2) {
         const int bits = fits_int16(ctx, P, o, cl.len, den_cache, env_bits) ? 16 : 32;
-        const int prune = wants_prune(P, o, Po, bits, con_begin[(size_t)c * n_org + o], prune_mode, prune_drop, prune_frac) ? 1 : 0;
+        const int prune = wants_prune(P, o, Po, bits, con_begin[(size_t)c * n_org + o], prune_mode_c, prune_drop, prune_frac) ? 1 : 0;
         fast_bucket[pick_fast(Po, bits, prune)].push_back(o);
         kmer_cap = std::max(kmer_cap, P.kmer_need[o]);
         ++n_fast_org;
@@ -897,7 +943,7 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
     // Splitting a length class's organisms of one arithmetic over a regular and a pruned launch pays only when both are
     // large enough to fill the machine a few times over; otherwise the launch tails cost more than the pruned stages
     // save and the smaller bucket joins the larger one (the pruned kernels run any organism: they decide per stage).
-    if (prune_mode == 1) {
+    if (prune_mode_c == 1) {
       const long long min_items = 4LL * n_sm;
       auto items_of = [&](int j) { return (long long)fast_bucket[j].size() * ((cl.count + 255) / 256); };
       for (int j = 0; j < kNumFastConfigs; ++j) {
