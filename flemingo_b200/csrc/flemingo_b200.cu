@@ -701,26 +701,21 @@ extern "C" int fl_update_connectors(fl_ctx *ctx, const double *con_pool, long lo
 // the spread of the combinatorial term den(g) (connector.c:51-56).  True when the packed 16-bit integer pass will
 // accept the organism at a scale of at least 32 units per energy unit (the device re-derives the plan from the real
 // ranges and hands the organism's pairs to the exact kernel should it disagree).
-static bool fits_int16(fl_ctx *ctx, const Population &P, int o, int S, std::map<long long, double> &den_cache, const char *force) {
+static bool fits_int16(fl_ctx *ctx, const Population &P, int o, int S, const char *force) {
   if (force) return atoi(force) == 16;
   const int rb = P.rec_begin[o], n = P.rec_begin[o + 1] - rb;
   static const bool shapes_too = getenv("FLEMINGO_16_SHAPES") != nullptr;   // experiment knob (see the comment above)
   if (n < 2 || (!P.pssm_only[o] && !shapes_too)) return false;
   const int Pn = S - P.sum_len[o] + 1, eff = S - P.sum_len[o] + n;
   if (Pn < 2 || eff > 10000) return false;
-  const long long key = ((long long)n << 32) | (unsigned)P.sum_len[o];
-  auto it = den_cache.find(key);
-  if (it == den_cache.end()) {
-    const double *D = ctx->h_den.data();
-    double lo = INFINITY, hi = -INFINITY;
-    for (int g = 0; g <= Pn - 2; ++g) {
-      const double den = (D[(eff - (g + 1)) - 1] - D[(n - 1) - 1] - D[eff - (g + 1) - (n - 1) - 1]) - (D[eff - 1] - D[n - 1] - D[eff - n - 1]);
-      lo = std::min(lo, den);
-      hi = std::max(hi, den);
-    }
-    it = den_cache.emplace(key, hi - lo).first;
-  }
-  const double gr = 50.0 + it->second;
+  // spread of the combinatorial term: den(g) = log C(eff - g - 1, n - 1) - log C(eff, n) falls monotonically with g, so its
+  // range over the legit gaps 0 .. Pn-2 is den(0) - den(Pn - 2)
+  const double *D = ctx->h_den.data();
+  auto den_at = [&](int g) {
+    return (D[(eff - (g + 1)) - 1] - D[(n - 1) - 1] - D[eff - (g + 1) - (n - 1) - 1]) - (D[eff - 1] - D[n - 1] - D[eff - n - 1]);
+  };
+  const double den_range = std::fabs(den_at(0) - den_at(Pn - 2));
+  const double gr = 50.0 + den_range + 0.02;   // DEN_EXPANSION is rounded to 0.01: monotone up to that
   double cum = P.rec_range[rb], need = 0.0;
   for (int c = 0; c < n - 1; ++c) {
     need = std::max(need, 2.0 * cum + gr);
@@ -923,17 +918,23 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
     fp.want_trace = trace ? 1 : 0;
     fp.has_unk = set.has_unk.as<unsigned char>();
     int kmer_cap = 0;
-    std::map<long long, double> den_cache;
     std::vector<int> exact_bucket[kNumTileSizes], fast_bucket[kNumFastConfigs];
     long long n_fast_org = 0;
     // by estimate: not on a length class with many low-complexity sequences (see low_complexity)
     const int prune_mode_c = (prune_mode == 1 && cl.low_share > 0.15f) ? 0 : prune_mode;
+    const bool small_class = n_cls > 1 && cl.count < 128 && prune_mode != 2 && !getenv("FLEMINGO_FAST_CFG");
     for (int o = 0; o < n_org; ++o) {
       const int Po = cl.len - P.sum_len[o] + 1;
       if (allow_fast && P.kmer_need[o] > 0 && P.kmer_need[o] <= 16384 && Po >= 2) {
-        const int bits = fits_int16(ctx, P, o, cl.len, den_cache, env_bits) ? 16 : 32;
-        const int prune = wants_prune(P, o, Po, bits, con_begin[(size_t)c * n_org + o], prune_mode_c, prune_drop, prune_frac) ? 1 : 0;
-        fast_bucket[pick_fast(Po, bits, prune)].push_back(o);
+        const int bits = fits_int16(ctx, P, o, cl.len, env_bits) ? 16 : 32;
+        if (small_class) {
+          // a class of a few sequences is bound by its launches, not by its DP cells: ONE configuration per arithmetic
+          // (the one of the largest P; a smaller P only wastes part of a tile) instead of one launch per (J, TEAM)
+          fast_bucket[pick_fast(Pmax, bits, 0)].push_back(o);
+        } else {
+          const int prune = wants_prune(P, o, Po, bits, con_begin[(size_t)c * n_org + o], prune_mode_c, prune_drop, prune_frac) ? 1 : 0;
+          fast_bucket[pick_fast(Po, bits, prune)].push_back(o);
+        }
         kmer_cap = std::max(kmer_cap, P.kmer_need[o]);
         ++n_fast_org;
       } else {
