@@ -727,10 +727,13 @@ static bool fits_int16(fl_ctx *ctx, const Population &P, int o, int S, const cha
 }
 
 // Which organisms take a kernel with pruned stages (dp_stage_pruned): those whose estimated stage costs there -- a tight
-// connector's stage pruned, the others in full at the pruned kernel's smaller tile -- stay below 0.9 of the full stages
+// connector's stage pruned, the others in full at the pruned kernel's smaller tile -- stay below 0.97 of the full stages
 // of the regular configuration.  The estimate uses sigma only (a Gaussian is within `drop` bits of its peak for
-// |g - mu| <= sigma sqrt(2 ln2 drop)) and fast_cost's unit, issue slots per pair; the kernel decides stage by stage from
-// the real tables, so a wrong guess costs time, never correctness.  mode: 0 never, 1 by estimate, 2 every organism (tests).
+// |g - mu| <= sigma sqrt(2 ln2 drop)) and fast_cost's unit, issue slots per pair: the peak tiles the plan would choose
+// times the cost of a fresh-loaded tile, plus the per-block bookkeeping (thresholds 0.9 / 0.97 / 1.05 measured: config 3
+// 150.1 ms each, config 4 279 / 259 / 259 ms).  The kernel decides stage by stage from the real tables, so a wrong guess
+// costs time, never correctness.
+// mode: 0 never, 1 by estimate, 2 every organism (tests).
 static bool wants_prune(const Population &P, int o, int Po, int bits, long long cb, int mode, int drop, int frac) {
   if (mode == 0) return false;
   const int rb = P.rec_begin[o], n = P.rec_begin[o + 1] - rb;
@@ -749,14 +752,19 @@ static bool wants_prune(const Population &P, int o, int Po, int bits, long long 
     const double sigma = P.con_sigma[rb + c];
     double stage = full_here;
     if (sigma >= 0.0) {
-      const double width = 2.0 * sigma * std::sqrt(1.3863 * drop) + 1.0;
-      const int tiles = (int)(width / J) + 2;
+      // the kernel's peak window: `drop` units, halved while it spans more than six tiles (build_fast_plan step E)
+      int tiles = 0;
+      for (int d = drop;; d >>= 1) {
+        const double width = 2.0 * sigma * std::sqrt(1.3863 * d) + 1.0;
+        tiles = (int)(width / J) + 2;
+        if (tiles - 1 <= 6 || d <= 2) break;
+      }
       if ((long long)(tiles + 2) * frac <= NB)
         stage = std::min(stage, rounds * (tiles * tile + 150.0 + 2.0 * J) * team / 32.0);
     }
     cost += stage;
   }
-  return cost <= 0.9 * (n - 1) * full_regular;
+  return cost <= 0.97 * (n - 1) * full_regular;
 }
 
 static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long *con_begin, int flags, double *energies,
@@ -845,7 +853,7 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
   const char *env_prune = getenv("FLEMINGO_PRUNE");
   const int prune_mode = env_prune ? atoi(env_prune) : 1;
   const int prune_drop = getenv("FLEMINGO_PRUNE_DROP") ? std::max(1, atoi(getenv("FLEMINGO_PRUNE_DROP"))) : 8;
-  const int prune_frac = getenv("FLEMINGO_PRUNE_FRAC") ? std::max(1, atoi(getenv("FLEMINGO_PRUNE_FRAC"))) : 3;
+  const int prune_frac = getenv("FLEMINGO_PRUNE_FRAC") ? std::max(1, atoi(getenv("FLEMINGO_PRUNE_FRAC"))) : 2;
   // several length classes: their launch chains are independent and go round-robin onto the lanes
   const int n_lanes = n_cls > 1 ? fl_ctx::kLanes : 1;
   if (n_lanes > 1) {
@@ -942,10 +950,10 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
       }
     }
     // Splitting a length class's organisms of one arithmetic over a regular and a pruned launch pays only when both are
-    // large enough to fill the machine a few times over; otherwise the launch tails cost more than the pruned stages
+    // large enough to fill the machine eight times over; otherwise the launch tails cost more than the pruned stages
     // save and the smaller bucket joins the larger one (the pruned kernels run any organism: they decide per stage).
     if (prune_mode_c == 1) {
-      const long long min_items = 4LL * n_sm;
+      const long long min_items = 8LL * n_sm;
       auto items_of = [&](int j) { return (long long)fast_bucket[j].size() * ((cl.count + 255) / 256); };
       for (int j = 0; j < kNumFastConfigs; ++j) {
         if (!kFastConfigs[j].prune || fast_bucket[j].empty()) continue;

@@ -583,11 +583,17 @@ __device__ void build_fast_plan(const FastParams &f, const OrgView &v, const Fas
               dstar = d;
             }
           }
-          const double dropd = (double)f.prune_drop * plan->scale;
-          const int drop = dropd < 1.0e9 ? (int)dropd : 1000000000;
+          // peak tiles: within prune_drop energy units of the maximum -- but at most six of them: for a wide connector
+          // the window is halved (down to 2 units) and the bound tests decide about the rest, which is what pays there
           int dlo = dstar, dhi = dstar;
-          while (dlo > 0 && gt[dlo - 1] >= best - drop) --dlo;
-          while (dhi + 1 < NB && gt[dhi + 1] >= best - drop) ++dhi;
+          for (int drop_units = f.prune_drop;; drop_units >>= 1) {
+            const double dropd = (double)drop_units * plan->scale;
+            const int drop = dropd < 1.0e9 ? (int)dropd : 1000000000;
+            dlo = dhi = dstar;
+            while (dlo > 0 && gt[dlo - 1] >= best - drop) --dlo;
+            while (dhi + 1 < NB && gt[dhi + 1] >= best - drop) ++dhi;
+            if (dhi - dlo + 1 <= 6 || drop_units <= 2) break;
+          }
           plan->dlo[c] = dlo;
           plan->dhi[c] = dhi;
           plan->prune[c] = ((dhi - dlo + 1 + 2) * f.prune_frac <= NB) ? 1 : 0;
