@@ -996,7 +996,7 @@ static int place_batch(fl_ctx *ctx, Population &P, SeqSet &set, const long long 
       // pruned kernels: gt + gtail behind every gap table, bmax + pmax per pair slot (odd stride: teams on distinct banks)
       fast_nb[j] = kFastConfigs[j].prune ? (Pmax + kFastConfigs[j].J - 1) / kFastConfigs[j].J : 0;
       fast_gq[j] = kGPad + Pmax + kGPad + 2 * fast_nb[j];
-      fast_bm[j] = kFastConfigs[j].prune ? ((2 * fast_nb[j]) | 1) : 0;
+      fast_bm[j] = kFastConfigs[j].prune ? ((2 * fast_nb[j] + fast_nb[j] / 4 + 2) | 1) : 0;
       int best_occ = 0;
       // multiples of four only: the DP stages are bound by the ALU pipe of each of the SM's four schedulers, so a
       // scheduler that holds one warp more than the others sets the pace (13 warps: 194 ms on config 3, 12 warps: 169 ms)

@@ -90,7 +90,7 @@ struct FastParams {
   // bounds gt[nb_max] and their suffix maxima gtail[nb_max]; per pair slot, block maxima and prefix maxima of the row
   int gt_off;         // offset of gt inside a connector's table (ints); gq_stride covers gt_off + 2 * nb_max
   int nb_max;         // row blocks of the largest organism of the launch: ceil(Pmax / J)
-  int bm_stride;      // ints per pair slot for bmax + pmax (>= 2 * nb_max; 0 in a launch without pruning)
+  int bm_stride;      // ints per pair slot for bmax + pmax + bmax of groups of four (>= 2 * nb_max + nb_max / 4 + 1; 0 in a launch without pruning)
   int prune_drop;     // a tile belongs to the peak while its bound is within this many energy units of the maximum
   int prune_frac;     // a stage is pruned when (peak tiles + 2) * prune_frac <= row blocks
 };
@@ -1209,7 +1209,7 @@ __global__ void __launch_bounds__(512, 1) place_fast_kernel(const FastParams f) 
             tabs.dlo = plan.dlo[i - 1];
             tabs.dhi = plan.dhi[i - 1];
             int *bm = sm.bm + (size_t)slot * f.bm_stride;
-            const int tiles_run = dp_stage_pruned<J, TEAM, RowT>(prev, cur, Gq, tabs, bm, bm + f.nb_max, P, tl);
+            const int tiles_run = dp_stage_pruned<J, TEAM, RowT>(prev, cur, Gq, tabs, bm, bm + f.nb_max, bm + 2 * f.nb_max, P, tl);
 #ifdef FL_PHASE_CLOCKS
             {   // tiles run / tiles of the full triangle / pruned pair-stages
               int sum = live ? (tiles_run & 0xffff) : 0;

@@ -515,17 +515,35 @@ struct PruneTabs {
 };
 
 // The next k block at or below kb (walking down) whose tile can still raise one of the maxima of row block b, given
-// the smallest of them so far; -1 when none is left.  Tiles dlo..dhi have been run already.
-__device__ __forceinline__ int prune_next_tile(int b, int kb, int minacc, const PruneTabs &tabs, const int *bm, const int *pm) {
+// the smallest of them so far; -1 when none is left.  Tiles dlo..dhi have been run already.  On the far side an aligned
+// group of four k blocks is skipped with one test (bm4 = maximum of the row over the four blocks; gtail[d] bounds the gap
+// energies of every tile at or beyond d): a single good predecessor far to the left keeps the prefix maximum high for
+// every block above it, and walking down to it block by block was 20 % of the pruned kernel's time.
+__device__ __forceinline__ int prune_next_tile(int b, int kb, int minacc, const PruneTabs &tabs, const int *bm, const int *pm,
+                                               const int *bm4) {
   while (kb >= 0) {
     const int d = b - kb;
     if (d >= tabs.dlo && d <= tabs.dhi) {
       kb = b - tabs.dhi - 1;
       continue;
     }
-    if (d > tabs.dhi && pm[kb] + tabs.gtail[d] <= minacc) return -1;  // nothing on the far side can matter any more
-    if (bm[kb] + tabs.gt[d] > minacc) break;
+    if (d > tabs.dhi) {
+      const int tail = tabs.gtail[d];
+      if (pm[kb] + tail <= minacc) return -1;  // nothing on the far side can matter any more
+      if (bm4 != nullptr && (kb & 3) == 3 && bm4[kb >> 2] + tail <= minacc) {
+        kb -= 4;
+        continue;
+      }
+    }
+    // two tiles per trip (their four loads in flight together: the walk is a chain of load -> add -> compare -> branch)
+    const int kb2 = kb > 0 ? kb - 1 : 0, d2 = b - kb2;
+    const int v1 = bm[kb] + tabs.gt[d], v2 = bm[kb2] + tabs.gt[d2];
+    if (v1 > minacc) break;
     --kb;
+    if (kb >= 0 && !(d2 >= tabs.dlo && d2 <= tabs.dhi)) {
+      if (v2 > minacc) break;
+      --kb;
+    }
   }
   return kb;
 }
@@ -572,7 +590,7 @@ __device__ __forceinline__ void prune_flush(const unsigned (&acc)[J], short *cur
 // Returns tiles this lane ran + 65536 * tile steps of the warp (statistics of the profiling build; dead code otherwise).
 template <int J, int TEAM, class RowT>
 __device__ __forceinline__ int dp_stage_pruned(const RowT *prev, RowT *cur, const int *__restrict__ G, const PruneTabs tabs,
-                                               int *bm, int *pm, int P, int tl) {
+                                               int *bm, int *pm, int *bm4, int P, int tl) {
   constexpr bool k16 = sizeof(RowT) == 2;
   constexpr int kLow = -0x7fffffff - 1;
   typedef typename std::conditional<k16, unsigned, int>::type AccT;
@@ -598,6 +616,18 @@ __device__ __forceinline__ int dp_stage_pruned(const RowT *prev, RowT *cur, cons
     carry = __shfl_sync(0xffffffffu, v, TEAM - 1, TEAM);
   }
   __syncwarp();
+  // maxima over aligned groups of four blocks: pays when there are many blocks (2 kb promoters: config 4 259 -> 251 ms),
+  // costs 2-3 % at 300 bp
+  const bool groups = NB >= 32;
+  if (groups) {
+    for (int q = tl; 4 * q < NB; q += TEAM) {
+      int v = bm[4 * q];
+#pragma unroll
+      for (int e = 1; e < 4; ++e) v = max(v, (4 * q + e < NB) ? bm[4 * q + e] : kLow);
+      bm4[q] = v;
+    }
+    __syncwarp();
+  }
   for (int hi = NB - 1; hi >= 0; hi -= TEAM) {
     const int b = hi - tl;   // < 0: idle lane of the last round
     AccT acc[J];
@@ -615,7 +645,7 @@ __device__ __forceinline__ int dp_stage_pruned(const RowT *prev, RowT *cur, cons
     // everything else, by bound
     int kb = b;
     for (;;) {
-      kb = prune_next_tile(b, kb, minacc, tabs, bm, pm);
+      kb = prune_next_tile(b, kb, minacc, tabs, bm, pm, groups ? bm4 : nullptr);
       if (!__any_sync(0xffffffffu, kb >= 0)) break;
       tiles_run += 65536;
       if (kb >= 0) {

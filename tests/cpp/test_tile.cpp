@@ -176,7 +176,7 @@ template <int J, int TEAM, bool K16> int run_pruned(int P, unsigned seed, int pr
   H[0] = pack16(G[0], SENT);
   const int *Gp = K16 ? reinterpret_cast<const int *>(H.data()) + kGPad : G.data() + kGPad;
   // step E of the plan
-  std::vector<int> gt(NB), gtail(NB), bm(NB), pm(NB);
+  std::vector<int> gt(NB), gtail(NB), bm(NB), pm(NB), bm4(NB / 4 + 1, -0x7fffffff - 1);
   for (int d = 0; d < NB; d++) {
     const int lo = std::max(0, (d - 1) * J + 1), hi = std::min(P - 2, (d + 1) * J - 1);
     int m = SENT;
@@ -202,6 +202,7 @@ template <int J, int TEAM, bool K16> int run_pruned(int P, unsigned seed, int pr
     bm[kb] = v;
     run = std::max(run, v);
     pm[kb] = run;
+    bm4[kb / 4] = std::max(bm4[kb / 4], v);
   }
   long long tiles = 0;
   RowT *buf = row.data();
@@ -216,7 +217,7 @@ template <int J, int TEAM, bool K16> int run_pruned(int P, unsigned seed, int pr
       int minacc = (tabs.dlo <= b) ? prune_row_min<J>(acc[tl], b, P) : -0x7fffffff - 1;
       int kb = b;
       for (;;) {
-        kb = prune_next_tile(b, kb, minacc, tabs, bm.data(), pm.data());
+        kb = prune_next_tile(b, kb, minacc, tabs, bm.data(), pm.data(), (seed & 1) ? bm4.data() : nullptr);
         if (kb < 0) break;
         prune_run_tile<J>(acc[tl], buf, Gp, b, kb);
         tiles++;
