@@ -455,9 +455,10 @@ __device__ __forceinline__ void dp_stage16(const short *prev, short *cur, const 
 // unconditionally, which lifts the J maxima to their final level or close to it, and then
 //   near side (delta < dlo): one bound test per tile;
 //   far side  (delta > dhi): first ONE test for the whole rest, pmax[kb] + gtail[delta] (prefix maximum of prev, suffix
-//                            maximum of gt), then tile by tile.
-// The per-connector tables gt / gtail / dlo / dhi come from the organism's plan; bmax / pmax are built here, per pair
-// and stage.  Row blocks are not folded (the work per block no longer grows with b): a round gives one block to each
+//                            maximum of gt), then -- for rows of 32 blocks or more -- one test per aligned group of four
+//                            k blocks (bmax of the group + gtail), then tile by tile.
+// The per-connector tables gt / gtail / dlo / dhi come from the organism's plan; bmax / pmax (and the group maxima) are
+// built here, per pair and stage.  Row blocks are not folded (the work per block no longer grows with b): a round gives one block to each
 // lane of the team, top blocks first, and flushes after the round -- lower rounds only read lower k blocks, so the
 // stage may run in place like dp_stage.  The lanes of a warp leave the tile loop together (ballot), whatever their
 // number of tiles.
