@@ -2,7 +2,7 @@
 src/organism.json has sigma = 0.44 on every connector; its config.json bounds sigma to [1, 3]) -- with and without
 the pruned DP stages (dp_stage_pruned), next to the factory's initial distribution sigma ~ Exp(S/12) of configs 2-5.
 
-    python tools/bench_tight.py > profiles/r2_pruned_stages.txt          (on the GPU box)
+    python tools/bench_tight.py > profiles/r2_pruned_stages.txt          (on the GPU box; any argument: 300 bp cases only)
 
 Device-timed with CUDA events on the engine's stream, best of 5; every case is first checked pair by pair against
 the exact kernel on a sample.
